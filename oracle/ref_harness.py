@@ -1,0 +1,186 @@
+"""Harness that imports the UNMODIFIED reference (read-only at /root/reference) in this container.
+
+TEST INFRASTRUCTURE ONLY — used by oracle/gen_golden.py to produce tests/golden/*.npz and by
+oracle/time_reference.py.  It never runs on the GPU box (/root/reference does not exist there)
+and nothing under roborugby_b200/ imports it.
+
+What it does:
+  * puts oracle/shims (stub pygame + gym) and the reference root on sys.path;
+  * selects the preset: the reference binds its constants at import time from one flag
+    (RR_Constants.py:4, GAME_MODE).  For the TRAIN preset the module source is read from the
+    read-only tree, the single flag line is flipped IN MEMORY and the module is installed in
+    sys.modules before the package imports it; no reference file is copied or written;
+  * works around the construction crash of the v0/v2 observers (RR_Observers.py:30-37,133-141)
+    by pre-seeding the class-level observation_space;
+  * extract()/inject() read and write the complete physics state of an env, including the
+    redundant, independently drifting FloatRect fields (MyUtils.py:141-148) and the one robot
+    history slot that is ever read (RR_Robot.py:43-58,110-137).
+
+State layout (all float64 unless noted), R robots, B balls:
+  rob[R, 7]   cx, cy, left, right, top, bottom, rot                 (FloatRect fields)
+  rhist[R, 3] x, y, rot of history slot (count-1)  (valid iff rflag[:,2])
+  rflag[R, 3] int32: thrust_l, thrust_r, hist_valid
+  ball[B, 8]  cx, cy, left, right, top, bottom, vx, vy
+  step        int32 lngStepCount
+"""
+import importlib
+import importlib.abc
+import importlib.machinery
+import importlib.util
+import os
+import sys
+
+REF_ROOT = os.environ.get("RR_REFERENCE_ROOT", "/root/reference")
+_SHIMS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shims")
+
+ENV_IDS = {
+    "RoboRugby-v0": ("robo_rugby.gym_env", "GameEnv"),
+    "RoboRugbySimple-v0": ("robo_rugby.gym_env.RR_Environments", "SimpleChasePos"),
+    "RoboRugbySimpleDuel-v2": ("robo_rugby.gym_env.RR_Environments", "SimpleDuel2"),
+    "RoboRugbySimpleDuel-v3": ("robo_rugby.gym_env.RR_Environments", "SimpleDuel3"),
+}
+
+
+def load_reference(preset):
+    """Import the reference with preset 'GAME' (as shipped) or 'TRAIN' (GAME_MODE=False)."""
+    assert preset in ("GAME", "TRAIN")
+    if "robo_rugby" in sys.modules:
+        raise RuntimeError("reference already imported in this process; constants bind at import")
+    if not os.path.isdir(REF_ROOT):
+        raise RuntimeError(f"reference tree not found at {REF_ROOT}")
+    for p in (REF_ROOT, _SHIMS):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    if preset == "TRAIN":
+        name = "robo_rugby.gym_env.RR_Constants"
+        path = os.path.join(REF_ROOT, "robo_rugby", "gym_env", "RR_Constants.py")
+
+        class _Loader(importlib.machinery.SourceFileLoader):
+            def get_data(self, p):
+                data = super().get_data(p)
+                if p == path:
+                    assert data.count(b"GAME_MODE = True") == 1
+                    data = data.replace(b"GAME_MODE = True", b"GAME_MODE = False")
+                return data
+
+            def get_code(self, fullname):  # never use or write a .pyc for the patched module
+                return self.source_to_code(self.get_data(path), path)
+
+        class _Finder(importlib.abc.MetaPathFinder):
+            def find_spec(self, fullname, p=None, target=None):
+                if fullname == name:
+                    return importlib.util.spec_from_file_location(name, path, loader=_Loader(name, path))
+                return None
+
+        sys.meta_path.insert(0, _Finder())
+    import robo_rugby  # noqa: F401  (registers the env ids with the stub gym)
+    const = importlib.import_module("robo_rugby.gym_env.RR_Constants")
+    assert const.GAME_MODE == (preset == "GAME")
+    return const
+
+
+def make_env(env_id, through_gym=False):
+    """Construct a reference env.  through_gym=True returns the TimeLimit-wrapped env."""
+    import gym
+    import numpy as np
+    from robo_rugby.gym_env.RR_EnvBase import GameEnv
+    const = importlib.import_module("robo_rugby.gym_env.RR_Constants")
+    if env_id in ("RoboRugbySimple-v0", "RoboRugbySimpleDuel-v2") and GameEnv.observation_space is None:
+        hi = max(const.ARENA_WIDTH, const.ARENA_HEIGHT, 360)
+        GameEnv.observation_space = gym.spaces.Box(-hi, hi, dtype=np.float32, shape=(5,))
+    if through_gym:
+        return gym.make(env_id)
+    mod, cls = ENV_IDS[env_id]
+    env = getattr(importlib.import_module(mod), cls)()
+    env.spec = gym.spec(env_id)
+    return env
+
+
+def reset_scratch():
+    """Put the module-global scratch rect (RR_TrashyPhysics.py:29-35) back to its import-time state.
+
+    Its centre is moved incrementally (cx += new - cx), so its low bits depend on every earlier
+    call in the process; golden records start from the pristine value so they are reproducible.
+    """
+    tp = importlib.import_module("robo_rugby.gym_env.RR_TrashyPhysics")
+    r = tp._rectBallInner
+    h = tp._dblHalfRadius_Rad2
+    r._dblCenterX = (-h + h) / 2
+    r._dblCenterY = (-h + h) / 2
+    r._dblLeft, r._dblRight, r._dblTop, r._dblBottom = -h, h, -h, h
+    r._dblRotation = 0
+    r._dctCornersRelCenter = r._dctInitialCornersRelCenter.copy()
+
+
+def extract(env):
+    import numpy as np
+    from robo_rugby.gym_env.RR_Robot import Robot
+    env = env.unwrapped
+    R, B = len(env.lstRobots), len(env.lstBalls)
+    rob = np.zeros((R, 7)); rhist = np.zeros((R, 3)); rflag = np.zeros((R, 3), np.int32)
+    for i, r in enumerate(env.lstRobots):
+        f = r.rectDbl
+        rob[i] = (f._dblCenterX, f._dblCenterY, f._dblLeft, f._dblRight, f._dblTop, f._dblBottom, f._dblRotation)
+        rflag[i, 0], rflag[i, 1] = r.lngLThrust, r.lngRThrust
+        slot = r._lstStates[(r.lngMoveCount - 1) % Robot._slngMoveHistorySize]
+        if slot is not None and slot[3] == r.lngMoveCount - 1:
+            rhist[i] = slot[:3]
+            rflag[i, 2] = 1
+    ball = np.zeros((B, 8))
+    for i, b in enumerate(env.lstBalls):
+        f = b.rectDbl
+        assert f._dblRotation == 0
+        ball[i] = (f._dblCenterX, f._dblCenterY, f._dblLeft, f._dblRight, f._dblTop, f._dblBottom,
+                   b.dbl_velocity_x, b.dbl_velocity_y)
+    return dict(rob=rob, rhist=rhist, rflag=rflag, ball=ball, step=np.int32(env.lngStepCount))
+
+
+def inject(env, st):
+    """Overwrite the env's physics state with `st` (same layout as extract()).
+
+    Fresh FloatRects are built so no alias to an older rect survives; the rotation setter is used
+    for the rotation-dependent corner table (a pure function of the stored angle,
+    MyUtils.py:277-322), then the centre and L/R/T/B doubles are written verbatim.
+    """
+    from MyUtils import FloatRect
+    from robo_rugby.gym_env.RR_Robot import Robot
+    const = importlib.import_module("robo_rugby.gym_env.RR_Constants")
+    env = env.unwrapped
+    for i, r in enumerate(env.lstRobots):
+        cx, cy, L, Rr, T, Bm, rot = (float(v) for v in st["rob"][i])
+        f = FloatRect(0, const.ROBOT_LENGTH, 0, const.ROBOT_WIDTH)
+        f.rotation = rot
+        assert f._dblRotation == rot or (rot == 0 and f._dblRotation == 0), (f._dblRotation, rot)
+        f._dblCenterX, f._dblCenterY = cx, cy
+        f._dblLeft, f._dblRight, f._dblTop, f._dblBottom = L, Rr, T, Bm
+        r.rectDbl = f
+        r.lngLThrust, r.lngRThrust = int(st["rflag"][i, 0]), int(st["rflag"][i, 1])
+        r.lngFrameMass = const.MASS_ROBOT
+        r._lstStates = [None] * Robot._slngMoveHistorySize
+        if int(st["rflag"][i, 2]):
+            # any count >= 1 is equivalent; use 1 so slot 0 holds the older pose
+            r.lngMoveCount = 1
+            hx, hy, hr = (float(v) for v in st["rhist"][i])
+            r._lstStates[0] = (hx, hy, hr, 0)
+        else:
+            r.lngMoveCount = 0
+        r.rectDblPriorStep = r.rectDbl.copy()
+    for i, b in enumerate(env.lstBalls):
+        cx, cy, L, Rr, T, Bm, vx, vy = (float(v) for v in st["ball"][i])
+        f = FloatRect(0, 2 * const.BALL_RADIUS, 0, 2 * const.BALL_RADIUS)
+        f._dblCenterX, f._dblCenterY = cx, cy
+        f._dblLeft, f._dblRight, f._dblTop, f._dblBottom = L, Rr, T, Bm
+        b.rectDbl = f
+        b.dbl_velocity_x, b.dbl_velocity_y = vx, vy
+        b.dbl_force_x = b.dbl_force_y = 0
+        b.lngFrameMass = const.MASS_BALL
+        b.bln_moved_cur_frame = False
+        b.rectDblPriorStep = b.rectDbl.copy()
+        b.rectDblPriorFrame = b.rectDbl.copy()
+    env.lngStepCount = int(st["step"])
+    for g in (env.sprHappyGoal, env.sprGrumpyGoal):
+        g.on_reset()
+    if hasattr(env, "set_naughty_bots"):
+        env.set_naughty_bots.clear()
+    if hasattr(env, "reward_happy"):
+        env.reward_happy = env.reward_grumpy = 0.0

@@ -1,0 +1,106 @@
+/* rr_oracle.h — CPU restatement of the RoboRugby reference step()/reset() path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  This library is the parity oracle: only tests/, the smoke check in
+ * __graft_entry__.py and the cpu_baseline / --impl reference legs of bench.py may load it.  The
+ * product (roborugby_b200/) never links, imports or calls it and has no CPU fallback.
+ *
+ * Parity status: PINNED.  The reference ships no tests or golden vectors; the
+ * oracle is pinned against outputs of the reference itself, executed in the build container by
+ * oracle/gen_golden.py (stub pygame/gym, unmodified reference sources) and committed under
+ * tests/golden/.  tests/test_oracle_golden.py requires bit-for-bit equality on every record.
+ *
+ * The restatement follows the reference object model (FloatRect with redundant, independently
+ * drifting centre/left/right/top/bottom doubles; robot pose history ring; module-global scratch
+ * rect) and its exact order of IEEE-754 double operations; it must be compiled with
+ * -ffp-contract=off and linked against the same libm CPython uses.
+ */
+#ifndef RR_ORACLE_H
+#define RR_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RRO_MAX_ROBOTS 8
+#define RRO_MAX_BALLS 16
+#define RRO_MAX_OBS 64
+
+/* reward mixins (RR_ScoreKeepers.py) */
+#define RRO_REW_CHASE 1u    /* ChasePosBall        :46-66   */
+#define RRO_REW_PUSHPOS 2u  /* PushPosBallsToGoal  :138-157 */
+#define RRO_REW_NAUGHTY 4u  /* NaughtyBots         :112-135 */
+
+/* observers (RR_Observers.py) */
+#define RRO_OBS_NONE 0
+#define RRO_OBS_BASIC_LIDAR 1 /* PosBall_BasicLidar      :116-166, 5 values  */
+#define RRO_OBS_LIDAR6_V2 2   /* SingleBall_6wayLidar_v2 :287-406, 11 values */
+#define RRO_OBS_ALLCOORDS 3   /* AllCoords               :47-83, 3R+2B values */
+
+/* error bits: the Python exceptions of the path */
+#define RRO_ERR_STEP_AFTER_DONE 1u      /* RR_EnvBase.py:261-262 */
+#define RRO_ERR_TOO_MANY_COMMANDS 2u    /* :270-271, :621-622    */
+#define RRO_ERR_BOT_COLLISIONS 4u       /* :312-313              */
+#define RRO_ERR_UNDO_FAILED 8u          /* :324-325              */
+#define RRO_ERR_ROBOTS_STUCK 16u        /* :327-330              */
+#define RRO_ERR_UNRESOLVED_FRAME 32u    /* :417-421              */
+#define RRO_ERR_COINCIDENT_BALLS 64u    /* RR_TrashyPhysics.py:249-250 */
+#define RRO_ERR_DIV0 128u               /* MyUtils.py:25         */
+
+typedef struct {
+  int arena_w, arena_h;      /* RR_Constants.py:6-7   */
+  int n_happy, n_grumpy;     /* :32-33                */
+  int n_pos, n_neg;          /* :30-31                */
+  int game_length_steps;     /* :25                   */
+  int game_mode;             /* :4 (only changes the behaviour at RR_EnvBase.py:417-421) */
+  uint32_t reward_mask;      /* RRO_REW_*             */
+  int observer;              /* RRO_OBS_*             */
+  int discrete;              /* 1: GameEnv_Simple.step (RR_EnvBase.py:617-626) */
+  int time_limit;            /* 1: gym TimeLimit semantics (done at step >= T), 0: raw (step > T) */
+} rro_config;
+
+typedef struct rro_env rro_env;
+
+void rro_default_config(rro_config *cfg, int game_mode, const char *env_id);
+rro_env *rro_create(const rro_config *cfg);
+void rro_destroy(rro_env *e);
+int rro_obs_dim(const rro_env *e);
+int rro_num_robots(const rro_env *e);
+int rro_num_balls(const rro_env *e);
+
+/* State layout = oracle/ref_harness.py extract(): rob[R][7], rhist[R][3], rflag[R][3], ball[B][8]. */
+void rro_set_state(rro_env *e, const double *rob, const double *rhist, const int32_t *rflag,
+                   const double *ball, int32_t step);
+void rro_get_state(const rro_env *e, double *rob, double *rhist, int32_t *rflag, double *ball,
+                   int32_t *step);
+
+/* One step.  `actions` holds n_actions values: discrete ids (as doubles) when cfg.discrete, else
+ * 2 thrust values per robot.  obs_h / obs_g receive obs_dim doubles (NaN-filled when the
+ * reference returns None).  rew[2] = happy, grumpy.  Returns the error mask (0 = ok). */
+uint32_t rro_step(rro_env *e, const double *actions, int n_actions, double *obs_h, double *obs_g,
+                  double *rew, int32_t *done, int32_t *naughty_count);
+
+/* Observation of the current state (get_game_state(int_team=...)); team = +1 happy, -1 grumpy. */
+uint32_t rro_observe(rro_env *e, int team, double *obs);
+
+/* reset(bln_randomize_pos) fed from an explicit stream of randint() results (RR_EnvBase.py:155-216).
+ * Returns the number of draws consumed, or -1 if the stream ran out. */
+int rro_reset_draws(rro_env *e, int randomize, const int32_t *draws, int n_draws);
+/* Same reset, drawing from the counter-based generator the CUDA product uses (Philox4x32-10,
+ * key = seed, counter = (env_index, episode, draw/4)); see include/rr_b200.h. */
+void rro_reset_philox(rro_env *e, uint64_t seed, uint64_t env_index, uint32_t episode);
+
+/* The reference keeps one module-global scratch rect whose centre is updated incrementally
+ * (RR_TrashyPhysics.py:29-35,54-55).  mode 0 = faithful (state carried between calls, what the
+ * Python process does); mode 1 = fresh (centre assigned exactly; what a batched simulator can
+ * do).  rro_scratch_reset() restores the import-time value. */
+void rro_scratch_mode(int fresh);
+void rro_scratch_reset(void);
+
+/* Philox4x32-10 exposed for the RNG known-answer test. */
+void rro_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,25 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def golden_files(pattern):
+    import glob
+    return sorted(glob.glob(os.path.join(GOLDEN, pattern)))
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import rr_oracle
+    rr_oracle.build()
+    return rr_oracle

@@ -1,0 +1,88 @@
+"""Pins the CPU oracle (oracle/rr_oracle.c) to the reference's own outputs, bit for bit.
+
+The golden files were produced by oracle/gen_golden.py from the unmodified reference.  Every
+record is replayed through the oracle twice: (a) as a trajectory from the first state only and
+(b) step by step from each recorded state.  State, observations, rewards, done and the naughty
+count must be IDENTICAL (np.array_equal on float64; NaN == NaN for absent observations).
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_files
+from golden_util import actions_at, parse_name, state_at, state_diff, states_equal
+
+ROLLOUTS = [f for f in golden_files("*.npz") if parse_name(f)[2] in ("random", "chase", "sticky", "inject")]
+
+
+def _eq(a, b):
+    return np.array_equal(np.asarray(a, np.float64), np.asarray(b, np.float64), equal_nan=True)
+
+
+@pytest.mark.parametrize("path", ROLLOUTS, ids=[p.split("/")[-1] for p in ROLLOUTS])
+def test_oracle_matches_reference_bitwise(oracle, path):
+    preset, env_id, kind = parse_name(path)
+    d = np.load(path)
+    n, T = d["act"].shape[:2]
+    env = oracle.OracleEnv(preset, env_id)
+    oracle.scratch_mode(0)
+    bad = []
+    for mode in ("trajectory", "per_step"):
+        for i in range(n):
+            env.set_state(state_at(d, i, 0))
+            for t in range(T):
+                if mode == "per_step" or d["restart"][i, t]:
+                    env.set_state(state_at(d, i, t))
+                oracle.scratch_reset()
+                out = env.step(actions_at(d, i, t))
+                got = env.get_state()
+                want = state_at(d, i, t + 1)
+                exc = bool(d["exc"][i, t])
+                ok = states_equal(got, want) if not exc else True
+                ok &= bool(out["err"] != 0) == exc
+                if not exc:
+                    ok &= _eq(out["obs_h"], d["obs_h"][i, t]) and _eq(out["obs_g"], d["obs_g"][i, t])
+                    ok &= _eq(out["rew"], d["rew"][i, t])
+                    ok &= out["done"] == int(d["done"][i, t]) and out["naughty"] == int(d["naughty"][i, t])
+                if not ok:
+                    bad.append((mode, i, t, state_diff(got, want), out["err"], exc))
+                    break
+    assert not bad, f"{len(bad)} mismatching records, first: {bad[:3]}"
+
+
+RESETS = golden_files("*_reset_*.npz")
+
+
+@pytest.mark.parametrize("path", RESETS, ids=[p.split("/")[-1] for p in RESETS])
+def test_oracle_reset_matches_reference(oracle, path):
+    preset, env_id, _ = parse_name(path)
+    d = np.load(path)
+    env = oracle.OracleEnv(preset, env_id)
+    for i in range(d["draws"].shape[0]):
+        env.set_state(state_at(d, i, 0))
+        nd = int(d["ndraws"][i])
+        used = env.reset_draws(d["draws"][i, :nd])
+        assert used == nd
+        got, want = env.get_state(), state_at(d, i, 1)
+        assert states_equal(got, want), (i, state_diff(got, want))
+        assert _eq(env.observe(1), d["obs_h"][i, 0])
+        assert _eq(env.observe(-1), d["obs_g"][i, 0])
+
+
+TL = golden_files("*_timelimit.npz")
+
+
+@pytest.mark.parametrize("path", TL, ids=[p.split("/")[-1] for p in TL])
+def test_oracle_done_semantics(oracle, path):
+    preset, env_id, _ = parse_name(path)
+    d = np.load(path)
+    T, s0 = int(d["T"]), int(d["start_step"])
+    for time_limit, want in ((True, d["wrapped_done"]), (False, d["raw_done"])):
+        env = oracle.OracleEnv(preset, env_id, time_limit=time_limit)
+        env.reset_philox(1, 0, 0)
+        st = env.get_state(); st["step"] = np.int32(s0)
+        env.set_state(st)
+        got = [env.step([0] )["done"] for _ in range(len(want))]
+        assert got == [int(x) for x in want]
+    # raw env: the step after done raises (RR_EnvBase.py:261-262)
+    assert bool(d["raised"]) and env.step([0])["err"] & 1
+    assert T == env.cfg.game_length_steps
