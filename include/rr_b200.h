@@ -1,0 +1,165 @@
+/* rr_b200.h — C ABI of the B200-native batched RoboRugby simulator (librr_b200.so).
+ *
+ * Drop-in boundary for ONE path of harman097/RoboRugby: robo_rugby.gym_env step()/reset()
+ * (SURVEY.md §8).  The reference has no FFI layer — its boundary is the gym 0.17 Env API of the
+ * classes registered in robo_rugby/__init__.py:4-34 — so each entry point below names the Python
+ * method it replaces.  roborugby_b200/ mirrors that Python surface on top of this ABI
+ * (INTEGRATION.md shows the ctypes stub a reference maintainer would add).
+ *
+ * Conventions
+ *   - plain C: opaque handle, raw pointers and sizes, no torch/C++ types;
+ *   - every function returns 0 on success, a negative RR_E_* code otherwise; rr_last_error()
+ *     returns a thread-local message;
+ *   - "dev" pointers are CUDA device pointers on the handle's device, "host" pointers are
+ *     ordinary (ideally pinned) host memory; `stream` is a cudaStream_t passed as void*
+ *     (NULL = legacy default stream);
+ *   - the handle owns the structure-of-arrays state in HBM; a handle is thread-compatible
+ *     (external synchronisation per handle), there is no global state;
+ *   - there is no CPU fallback: if no CUDA device is usable rr_create fails.
+ *
+ * Batch layouts (N = n_envs, R = robots, B = balls, D = obs_dim, K = k_steps)
+ *   actions  discrete: uint8  [K][N][A]  A = n_actions <= R     (GameEnv_Simple.Direction ids 0..7)
+ *            continuous: float [K][N][A]  A = n_actions <= 2R    (left,right thrust per robot)
+ *   obs_h/g  out_t [K][N][D]     rew out_t [K][N][2] (happy, grumpy)     done uint8 [K][N]
+ *   out_t = float (default, the dtype the reference declares for observation_space,
+ *   RR_Observers.py:36-37) or double when cfg.out_f64 (the dtype its arrays actually hold).
+ */
+#ifndef RR_B200_H
+#define RR_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RR_ABI_VERSION 1
+
+/* presets == the two constant sets behind RR_Constants.py:4 (GAME_MODE) */
+#define RR_PRESET_GAME 0  /* 800x800, 2+2 robots, 4+4 balls, 4500 steps */
+#define RR_PRESET_TRAIN 1 /* 600x600, 1+0 robots, 1+0 balls, 300 steps  */
+
+/* reward mixins, RR_ScoreKeepers.py */
+#define RR_REW_CHASE 1u   /* ChasePosBall :46-66         */
+#define RR_REW_PUSHPOS 2u /* PushPosBallsToGoal :138-157 */
+#define RR_REW_NAUGHTY 4u /* NaughtyBots :112-135        */
+
+/* observers, RR_Observers.py */
+#define RR_OBS_NONE 0
+#define RR_OBS_BASIC_LIDAR 1 /* PosBall_BasicLidar :116-166 (5)        */
+#define RR_OBS_LIDAR6_V2 2   /* SingleBall_6wayLidar_v2 :287-406 (11)  */
+#define RR_OBS_ALLCOORDS 3   /* AllCoords :47-83 (3R+2B)               */
+
+/* per-env error bits == the Python exceptions of the path */
+#define RR_ERR_STEP_AFTER_DONE 1u   /* RR_EnvBase.py:261-262 */
+#define RR_ERR_TOO_MANY_COMMANDS 2u /* :270-271, :621-622    */
+#define RR_ERR_BOT_COLLISIONS 4u    /* :312-313              */
+#define RR_ERR_UNDO_FAILED 8u       /* :324-325              */
+#define RR_ERR_ROBOTS_STUCK 16u     /* :327-330              */
+#define RR_ERR_UNRESOLVED_FRAME 32u /* :417-421              */
+#define RR_ERR_COINCIDENT_BALLS 64u /* RR_TrashyPhysics.py:249-250 */
+#define RR_ERR_DIV0 128u            /* MyUtils.py:25         */
+#define RR_ERR_RESET_PLACEMENT 256u /* placement loop exceeded its bound (reference: unbounded) */
+
+/* return codes */
+#define RR_OK 0
+#define RR_E_INVALID (-1)
+#define RR_E_CUDA (-2)
+#define RR_E_NOMEM (-3)
+
+/* statistics vector (doubles), see rr_get_stats */
+#define RR_STAT_EPISODES 0
+#define RR_STAT_RETURN_HAPPY 1
+#define RR_STAT_RETURN_GRUMPY 2
+#define RR_STAT_LENGTH 3
+#define RR_STAT_NAUGHTY 4
+#define RR_STAT_ERRORS 5
+#define RR_STAT_STEPS 6
+#define RR_NUM_STATS 8
+
+typedef struct rr_config {
+  int32_t abi_version;  /* RR_ABI_VERSION */
+  int32_t preset;       /* RR_PRESET_*  (entity counts are compile-time in the kernels) */
+  uint32_t reward_mask; /* RR_REW_*     (class composition of RR_Environments.py:11-37) */
+  int32_t observer;     /* RR_OBS_* */
+  int32_t discrete;     /* 1: GameEnv_Simple.step :617-626, 0: GameEnv.step :260-297 */
+  int32_t time_limit;   /* 1: done at step >= T (gym TimeLimit via robo_rugby/__init__.py), 0: raw step > T */
+  int32_t auto_reset;   /* 1: an env that reports done (or raises) is reset inside the same launch */
+  int32_t out_f64;      /* 0: float outputs, 1: double outputs */
+  int32_t strict_reset; /* 1: reference placement test verbatim (may leave two balls exactly 14 px
+                           apart, a state in which the reference itself never returns);
+                           0: additionally reject such ball pairs */
+  int32_t reserved;
+  uint64_t seed;        /* Philox key */
+  int64_t env_offset;   /* global index of this handle's env 0 (rank * n_envs when sharded) */
+} rr_config;
+
+typedef struct rr_sim rr_sim;
+
+/* Fill cfg for one of the registered ids (robo_rugby/__init__.py:4-34):
+ * "RoboRugby-v0", "RoboRugbySimple-v0", "RoboRugbySimpleDuel-v2", "RoboRugbySimpleDuel-v3". */
+int rr_default_config(rr_config *cfg, int preset, const char *env_id);
+
+/* GameEnv.__init__ (RR_EnvBase.py:70-123) for n_envs episodes on CUDA device `device`. */
+int rr_create(const rr_config *cfg, int64_t n_envs, int device, rr_sim **out);
+int rr_destroy(rr_sim *s);
+const char *rr_last_error(void);
+
+int rr_num_envs(const rr_sim *s, int64_t *n);
+int rr_num_robots(const rr_sim *s);
+int rr_num_balls(const rr_sim *s);
+int rr_obs_dim(const rr_sim *s);      /* observation_space.shape[0] */
+int rr_max_steps(const rr_sim *s);    /* spec.max_episode_steps = GAME_LENGTH_STEPS */
+
+/* GameEnv.reset(bln_randomize_pos=True) (RR_EnvBase.py:202-216) for the envs whose mask byte is
+ * non-zero (mask_dev == NULL: all).  Random placement follows :155-200 with a counter-based
+ * generator (Philox4x32-10, key = seed, counter = (global env index, episode, draw/4)). */
+int rr_reset(rr_sim *s, const uint8_t *mask_dev, void *stream);
+
+/* get_game_state(int_team=HAPPY / GRUMPY) of the current state (RR_Observers.py). */
+int rr_observe(rr_sim *s, void *obs_h_dev, void *obs_g_dev, void *stream);
+
+/* step() x k_steps in ONE fused kernel launch; device buffers (layouts above).  Any output
+ * pointer may be NULL.  n_actions = values supplied per env per step (robots beyond it keep
+ * their thrust, RR_EnvBase.py:272-273). */
+int rr_step(rr_sim *s, const void *actions_dev, int32_t n_actions, int32_t k_steps, void *obs_h_dev,
+            void *obs_g_dev, void *rew_dev, uint8_t *done_dev, void *stream);
+
+/* Same call with HOST buffers: copies actions host->device, launches, copies results back and
+ * synchronises the stream before returning.  This is what a single-process caller of the
+ * reference's env.step() would bind. */
+int rr_step_host(rr_sim *s, const void *actions_host, int32_t n_actions, int32_t k_steps,
+                 void *obs_h_host, void *obs_g_host, void *rew_host, uint8_t *done_host, void *stream);
+
+/* Complete physics state, HOST buffers, array-of-structs layout used by the parity harness
+ * (oracle/ref_harness.py): rob[N][R][7] = cx,cy,left,right,top,bottom,rot (FloatRect fields,
+ * MyUtils.py:122-130); rhist[N][R][3] = pose in history slot count-1 (RR_Robot.py:43-58);
+ * rflag[N][R][3] = thrust_l, thrust_r, hist_valid; ball[N][B][8] = cx,cy,l,r,t,b,vx,vy;
+ * step[N] = lngStepCount.  These synchronise the device. */
+int rr_set_state(rr_sim *s, const double *rob, const double *rhist, const int32_t *rflag,
+                 const double *ball, const int32_t *step);
+int rr_get_state(rr_sim *s, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step);
+
+/* Per-env sticky error mask (RR_ERR_*) to HOST; clear != 0 zeroes it afterwards. */
+int rr_error_mask(rr_sim *s, uint32_t *err_host, int32_t clear);
+/* Naughty-robot count of the last step per env (len(set_naughty_bots)), to HOST. */
+int rr_last_naughty(rr_sim *s, int32_t *count_host);
+
+/* Episode statistics accumulated on the device since the last rr_clear_stats: RR_NUM_STATS doubles
+ * (finished episodes, sum of happy/grumpy returns, sum of lengths, naughty events, errors, steps).
+ * rr_stats_device_ptr exposes the device vector so a caller can all-reduce it in place (NCCL). */
+int rr_get_stats(rr_sim *s, double *stats_host);
+int rr_stats_device_ptr(rr_sim *s, double **stats_dev);
+int rr_clear_stats(rr_sim *s, void *stream);
+/* Accumulate into a caller-owned device vector of RR_NUM_STATS doubles instead (e.g. a torch tensor
+ * that torch.distributed all-reduces over NCCL); NULL restores the internal vector. */
+int rr_set_stats_buffer(rr_sim *s, double *stats_dev);
+
+/* Kernels launched by this handle so far (bench.py's gpu_launches). */
+int64_t rr_launch_count(const rr_sim *s);
+/* Bytes of persistent per-env state in HBM (S in DESIGN.md's roofline formula). */
+int64_t rr_state_bytes_per_env(const rr_sim *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

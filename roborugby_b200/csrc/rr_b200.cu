@@ -1,0 +1,589 @@
+// rr_b200.cu — kernels and C ABI (include/rr_b200.h) of the B200-native batched RoboRugby simulator.
+//
+// Build (see __graft_entry__.build()):
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo --fmad=false
+//        -Xcompiler -fPIC -shared -o roborugby_b200/librr_b200.so roborugby_b200/csrc/rr_b200.cu
+//
+// HBM layout: structure of arrays, env index fastest.
+//   sf : double [NF][N]   per robot cx,cy,left,right,top,bottom,rot,hx,hy,hrot ; per ball
+//                         cx,cy,left,right,top,bottom,vx,vy ; episode return happy, grumpy
+//   si : int32  [NI][N]   per robot (thrust_l & 0xff) | (thrust_r & 0xff) << 8 | hist_valid << 16 ;
+//                         step, episode, sticky error mask, naughty count of the last step
+// One thread owns one env for a whole launch: it loads its column of sf/si with coalesced 8-byte /
+// 4-byte transactions, advances k_steps env-steps (12 physics frames each) out of registers / L1,
+// streams actions in and observations, rewards and done flags out per step, and writes the column
+// back once.  No inter-thread communication is needed except the warp-shuffle reduction of the
+// episode statistics at the end of the launch.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "rr_sim.cuh"
+
+namespace rr {
+
+constexpr int kBlock = 128;
+
+template <int NH, int NG, int NP, int NN>
+struct Layout {
+  static constexpr int R = NH + NG, B = NP + NN;
+  static constexpr int kRobotF = 10, kBallF = 8;
+  static constexpr int NF = R * kRobotF + B * kBallF + 2;
+  static constexpr int NI = R + 4;
+};
+
+template <int NH, int NG, int NP, int NN>
+__device__ __forceinline__ void load_env(Env<NH, NG, NP, NN> &e, const Consts &k, const double *__restrict__ sf,
+                                         const int32_t *__restrict__ si, int64_t N, int64_t i) {
+  using L = Layout<NH, NG, NP, NN>;
+  int f = 0;
+  e.hvalid = 0;
+#pragma unroll
+  for (int r = 0; r < L::R; r++) {
+    e.rcx[r] = sf[(f + 0) * N + i]; e.rcy[r] = sf[(f + 1) * N + i];
+    e.rl[r] = sf[(f + 2) * N + i];  e.rr[r] = sf[(f + 3) * N + i];
+    e.rt[r] = sf[(f + 4) * N + i];  e.rb[r] = sf[(f + 5) * N + i];
+    e.rrot[r] = sf[(f + 6) * N + i];
+    e.hx[r] = sf[(f + 7) * N + i];  e.hy[r] = sf[(f + 8) * N + i]; e.hrot[r] = sf[(f + 9) * N + i];
+    f += L::kRobotF;
+    int32_t p = si[r * N + i];
+    e.thl[r] = (int)(int8_t)(p & 0xff);
+    e.thr[r] = (int)(int8_t)((p >> 8) & 0xff);
+    e.hvalid |= ((p >> 16) & 1u) << r;
+    robot_refresh_corners(e, k, r);
+  }
+#pragma unroll
+  for (int b = 0; b < L::B; b++) {
+    e.bcx[b] = sf[(f + 0) * N + i]; e.bcy[b] = sf[(f + 1) * N + i];
+    e.bl[b] = sf[(f + 2) * N + i];  e.br[b] = sf[(f + 3) * N + i];
+    e.bt[b] = sf[(f + 4) * N + i];  e.bb[b] = sf[(f + 5) * N + i];
+    e.bvx[b] = sf[(f + 6) * N + i]; e.bvy[b] = sf[(f + 7) * N + i];
+    f += L::kBallF;
+  }
+  e.ret_h = sf[(f + 0) * N + i]; e.ret_g = sf[(f + 1) * N + i];
+  e.step = si[(L::R + 0) * N + i];
+  e.episode = (unsigned)si[(L::R + 1) * N + i];
+  e.err = (unsigned)si[(L::R + 2) * N + i];
+}
+
+template <int NH, int NG, int NP, int NN>
+__device__ __forceinline__ void store_env(const Env<NH, NG, NP, NN> &e, double *__restrict__ sf, int32_t *__restrict__ si,
+                                          int64_t N, int64_t i, int last_naughty) {
+  using L = Layout<NH, NG, NP, NN>;
+  int f = 0;
+#pragma unroll
+  for (int r = 0; r < L::R; r++) {
+    sf[(f + 0) * N + i] = e.rcx[r]; sf[(f + 1) * N + i] = e.rcy[r];
+    sf[(f + 2) * N + i] = e.rl[r];  sf[(f + 3) * N + i] = e.rr[r];
+    sf[(f + 4) * N + i] = e.rt[r];  sf[(f + 5) * N + i] = e.rb[r];
+    sf[(f + 6) * N + i] = e.rrot[r];
+    sf[(f + 7) * N + i] = e.hx[r];  sf[(f + 8) * N + i] = e.hy[r]; sf[(f + 9) * N + i] = e.hrot[r];
+    f += L::kRobotF;
+    si[r * N + i] = (e.thl[r] & 0xff) | ((e.thr[r] & 0xff) << 8) | (((e.hvalid >> r) & 1u) << 16);
+  }
+#pragma unroll
+  for (int b = 0; b < L::B; b++) {
+    sf[(f + 0) * N + i] = e.bcx[b]; sf[(f + 1) * N + i] = e.bcy[b];
+    sf[(f + 2) * N + i] = e.bl[b];  sf[(f + 3) * N + i] = e.br[b];
+    sf[(f + 4) * N + i] = e.bt[b];  sf[(f + 5) * N + i] = e.bb[b];
+    sf[(f + 6) * N + i] = e.bvx[b]; sf[(f + 7) * N + i] = e.bvy[b];
+    f += L::kBallF;
+  }
+  sf[(f + 0) * N + i] = e.ret_h; sf[(f + 1) * N + i] = e.ret_g;
+  si[(L::R + 0) * N + i] = e.step;
+  si[(L::R + 1) * N + i] = (int32_t)e.episode;
+  si[(L::R + 2) * N + i] = (int32_t)e.err;
+  si[(L::R + 3) * N + i] = last_naughty;
+}
+
+struct StepArgs {
+  double *sf;
+  int32_t *si;
+  double *stats;
+  const void *actions;  // uint8 or float [K][N][A]
+  void *obs_h, *obs_g, *rew;
+  uint8_t *done;
+  int64_t N;
+  int K;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// The fused multi-step kernel: K env-steps per launch, auto-reset inside.
+template <int NH, int NG, int NP, int NN, typename OutT>
+__global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ Consts k, const __grid_constant__ StepArgs a) {
+  using E = Env<NH, NG, NP, NN>;
+  constexpr int R = E::R;
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  const bool live = i < a.N;
+  double st[RR_NUM_STATS];
+#pragma unroll
+  for (int q = 0; q < RR_NUM_STATS; q++) st[q] = 0.0;
+  if (live) {
+    E e;
+    load_env(e, k, a.sf, a.si, a.N, i);
+    const int dim = obs_dim_of<NH, NG, NP, NN>(k.observer);
+    const int A = k.n_actions;
+    int last_naughty = 0;
+    for (int s = 0; s < a.K; s++) {
+      const int64_t row = (int64_t)s * a.N + i;
+      int cl[R], cr[R], n_cmd;
+      if (k.discrete) {
+        const uint8_t *ap = (const uint8_t *)a.actions + row * A;
+        n_cmd = A;
+        if (A == 4 && R >= 4) {  // one coalesced 32-bit load per env
+          uint32_t w = *(const uint32_t *)ap;
+#pragma unroll
+          for (int r = 0; r < 4 && r < R; r++) thrust_from_direction((w >> (8 * r)) & 0xff, cl[r], cr[r]);
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; r++)
+            if (r < A) thrust_from_direction(ap[r], cl[r], cr[r]);
+        }
+      } else {
+        const float *ap = (const float *)a.actions + row * A;
+        n_cmd = A / 2;
+#pragma unroll
+        for (int r = 0; r < R; r++)
+          if (r < n_cmd) {  // int(round(x)): round half to even (RR_Robot.py:100-102)
+            cl[r] = (int)rint((double)ap[2 * r]);
+            cr[r] = (int)rint((double)ap[2 * r + 1]);
+          }
+      }
+      StepOut o;
+      sim_step(e, k, cl, cr, n_cmd, o);
+      e.ret_h += o.rew_h; e.ret_g += o.rew_g;
+      last_naughty = rr_popc(o.naughty);
+      st[RR_STAT_STEPS] += 1.0;
+      st[RR_STAT_NAUGHTY] += (double)last_naughty;
+      const bool aborted = o.step_err != 0;
+      if (aborted) st[RR_STAT_ERRORS] += 1.0;
+      const int done = (o.done || aborted) ? 1 : 0;
+      if (done) {
+        st[RR_STAT_EPISODES] += 1.0;
+        st[RR_STAT_RETURN_HAPPY] += e.ret_h; st[RR_STAT_RETURN_GRUMPY] += e.ret_g;
+        st[RR_STAT_LENGTH] += (double)e.step;
+        if (k.auto_reset) {
+          e.episode += 1;
+          reset_env(e, k, (uint64_t)(k.env_offset + i));
+        }
+      }
+      if (a.rew) { ((OutT *)a.rew)[row * 2] = (OutT)o.rew_h; ((OutT *)a.rew)[row * 2 + 1] = (OutT)o.rew_g; }
+      if (a.done) a.done[row] = (uint8_t)done;
+      if (dim > 0 && (a.obs_h || a.obs_g)) {
+        double ob[kMaxObs];
+        unsigned oerr = 0;
+        if (a.obs_h) {
+          observe(e, k, 1, ob, oerr);
+          OutT *dst = (OutT *)a.obs_h + row * dim;
+          for (int q = 0; q < dim; q++) dst[q] = (OutT)ob[q];
+        }
+        if (a.obs_g) {
+          observe(e, k, -1, ob, oerr);
+          OutT *dst = (OutT *)a.obs_g + row * dim;
+          for (int q = 0; q < dim; q++) dst[q] = (OutT)ob[q];
+        }
+      }
+    }
+    store_env(e, a.sf, a.si, a.N, i, last_naughty);
+  }
+  // episode statistics: warp-shuffle reduction, one atomic per warp and statistic
+#pragma unroll
+  for (int q = 0; q < RR_NUM_STATS; q++) {
+    double v = warp_sum(st[q]);
+    if ((threadIdx.x & 31) == 0 && v != 0.0) atomicAdd(&a.stats[q], v);
+  }
+}
+
+template <int NH, int NG, int NP, int NN>
+__global__ void __launch_bounds__(kBlock) k_init(const __grid_constant__ Consts k, double *sf, int32_t *si, int64_t N) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= N) return;
+  Env<NH, NG, NP, NN> e;
+  construct_env(e);
+  reset_env(e, k, (uint64_t)(k.env_offset + i));
+  store_env(e, sf, si, N, i, 0);
+}
+
+template <int NH, int NG, int NP, int NN>
+__global__ void __launch_bounds__(kBlock) k_reset(const __grid_constant__ Consts k, double *sf, int32_t *si, int64_t N,
+                                                  const uint8_t *mask) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= N) return;
+  if (mask && !mask[i]) return;
+  Env<NH, NG, NP, NN> e;
+  load_env(e, k, sf, si, N, i);
+  e.episode += 1;
+  reset_env(e, k, (uint64_t)(k.env_offset + i));
+  store_env(e, sf, si, N, i, 0);
+}
+
+template <int NH, int NG, int NP, int NN, typename OutT>
+__global__ void __launch_bounds__(kBlock) k_observe(const __grid_constant__ Consts k, const double *sf, const int32_t *si,
+                                                    int64_t N, void *obs_h, void *obs_g) {
+  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= N) return;
+  Env<NH, NG, NP, NN> e;
+  load_env(e, k, sf, si, N, i);
+  const int dim = obs_dim_of<NH, NG, NP, NN>(k.observer);
+  double ob[kMaxObs];
+  unsigned oerr = 0;
+  if (obs_h) {
+    observe(e, k, 1, ob, oerr);
+    for (int q = 0; q < dim; q++) ((OutT *)obs_h)[i * dim + q] = (OutT)ob[q];
+  }
+  if (obs_g) {
+    observe(e, k, -1, ob, oerr);
+    for (int q = 0; q < dim; q++) ((OutT *)obs_g)[i * dim + q] = (OutT)ob[q];
+  }
+}
+
+}  // namespace rr
+
+// =============================================================================================
+// C ABI
+
+using namespace rr;
+
+struct rr_sim {
+  rr_config cfg;
+  Consts k;
+  int64_t N;
+  int device;
+  int NH, NG, NP, NN, R, B, NF, NI;
+  double *sf = nullptr;
+  int32_t *si = nullptr;
+  double *stats = nullptr;      // where kernels accumulate (own_stats or a caller buffer)
+  double *own_stats = nullptr;
+  // staging for rr_step_host
+  void *d_act = nullptr, *d_obs_h = nullptr, *d_obs_g = nullptr, *d_rew = nullptr;
+  uint8_t *d_done = nullptr;
+  size_t cap_act = 0, cap_obs_h = 0, cap_obs_g = 0, cap_rew = 0, cap_done = 0;
+  int64_t launches = 0;
+};
+
+static thread_local std::string g_err;
+const char *rr_last_error(void) { return g_err.c_str(); }
+
+static int fail(int code, const std::string &msg) {
+  g_err = msg;
+  return code;
+}
+#define CK(call)                                                                               \
+  do {                                                                                         \
+    cudaError_t _e = (call);                                                                   \
+    if (_e != cudaSuccess)                                                                     \
+      return fail(RR_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(_e));              \
+  } while (0)
+
+int rr_default_config(rr_config *c, int preset, const char *env_id) {
+  if (!c || !env_id) return fail(RR_E_INVALID, "null argument");
+  std::memset(c, 0, sizeof *c);
+  c->abi_version = RR_ABI_VERSION;
+  c->preset = preset;
+  c->discrete = 1;
+  std::string id(env_id);
+  if (id == "RoboRugby-v0") {  // robo_rugby/__init__.py:4-10 -> GameEnv: no reward mixin, no observer
+    c->discrete = 0; c->reward_mask = 0; c->observer = RR_OBS_NONE;
+  } else if (id == "RoboRugbySimple-v0") {  // :12-18 -> SimpleChasePos (RR_Environments.py:11)
+    c->reward_mask = RR_REW_CHASE; c->observer = RR_OBS_BASIC_LIDAR;
+  } else if (id == "RoboRugbySimpleDuel-v2") {  // :20-26 -> SimpleDuel2 (RR_Environments.py:19-25)
+    c->reward_mask = RR_REW_CHASE | RR_REW_PUSHPOS | RR_REW_NAUGHTY; c->observer = RR_OBS_BASIC_LIDAR;
+  } else if (id == "RoboRugbySimpleDuel-v3") {  // :28-34 -> SimpleDuel3 (RR_Environments.py:27-37)
+    c->reward_mask = RR_REW_CHASE | RR_REW_PUSHPOS | RR_REW_NAUGHTY; c->observer = RR_OBS_LIDAR6_V2;
+  } else {
+    return fail(RR_E_INVALID, "unknown env id " + id);
+  }
+  c->auto_reset = 1;
+  c->time_limit = 1;
+  return RR_OK;
+}
+
+static inline unsigned grid_for(int64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+
+#define DISPATCH_PRESET(s, CALL)                 \
+  do {                                           \
+    if ((s)->cfg.preset == RR_PRESET_GAME) {     \
+      constexpr int NH = 2, NG = 2, NP = 4, NN = 4; \
+      CALL;                                      \
+    } else {                                     \
+      constexpr int NH = 1, NG = 0, NP = 1, NN = 0; \
+      CALL;                                      \
+    }                                            \
+  } while (0)
+
+int rr_create(const rr_config *cfg, int64_t n_envs, int device, rr_sim **out) {
+  if (!cfg || !out || n_envs <= 0) return fail(RR_E_INVALID, "bad arguments");
+  if (cfg->abi_version != RR_ABI_VERSION) return fail(RR_E_INVALID, "abi_version mismatch");
+  if (cfg->preset != RR_PRESET_GAME && cfg->preset != RR_PRESET_TRAIN) return fail(RR_E_INVALID, "unknown preset");
+  if (cfg->observer < 0 || cfg->observer > RR_OBS_ALLCOORDS) return fail(RR_E_INVALID, "unknown observer");
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    return fail(RR_E_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(ce));
+  if (device < 0 || device >= ndev) return fail(RR_E_INVALID, "device index out of range");
+  CK(cudaSetDevice(device));
+  rr_sim *s = new (std::nothrow) rr_sim();
+  if (!s) return fail(RR_E_NOMEM, "host allocation failed");
+  s->cfg = *cfg;
+  s->k = make_consts(*cfg);
+  s->N = n_envs;
+  s->device = device;
+  const bool game = cfg->preset == RR_PRESET_GAME;
+  s->NH = game ? 2 : 1; s->NG = game ? 2 : 0; s->NP = game ? 4 : 1; s->NN = game ? 4 : 0;
+  s->R = s->NH + s->NG; s->B = s->NP + s->NN;
+  s->NF = s->R * 10 + s->B * 8 + 2;
+  s->NI = s->R + 4;
+  if (cudaMalloc(&s->sf, sizeof(double) * s->NF * n_envs) != cudaSuccess ||
+      cudaMalloc(&s->si, sizeof(int32_t) * s->NI * n_envs) != cudaSuccess ||
+      cudaMalloc(&s->own_stats, sizeof(double) * RR_NUM_STATS) != cudaSuccess) {
+    cudaGetLastError();
+    rr_destroy(s);
+    return fail(RR_E_NOMEM, "device allocation failed");
+  }
+  s->stats = s->own_stats;
+  CK(cudaMemset(s->stats, 0, sizeof(double) * RR_NUM_STATS));
+  DISPATCH_PRESET(s, (k_init<NH, NG, NP, NN><<<grid_for(n_envs), kBlock>>>(s->k, s->sf, s->si, s->N)));
+  s->launches++;
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  *out = s;
+  return RR_OK;
+}
+
+int rr_destroy(rr_sim *s) {
+  if (!s) return RR_OK;
+  cudaSetDevice(s->device);
+  cudaFree(s->sf); cudaFree(s->si); cudaFree(s->own_stats);
+  cudaFree(s->d_act); cudaFree(s->d_obs_h); cudaFree(s->d_obs_g); cudaFree(s->d_rew); cudaFree(s->d_done);
+  delete s;
+  return RR_OK;
+}
+
+int rr_num_envs(const rr_sim *s, int64_t *n) { if (!s || !n) return fail(RR_E_INVALID, "null"); *n = s->N; return RR_OK; }
+int rr_num_robots(const rr_sim *s) { return s ? s->R : RR_E_INVALID; }
+int rr_num_balls(const rr_sim *s) { return s ? s->B : RR_E_INVALID; }
+int rr_max_steps(const rr_sim *s) { return s ? s->k.T : RR_E_INVALID; }
+int rr_obs_dim(const rr_sim *s) {
+  if (!s) return RR_E_INVALID;
+  switch (s->cfg.observer) {
+    case RR_OBS_BASIC_LIDAR: return 5;
+    case RR_OBS_LIDAR6_V2: return 11;
+    case RR_OBS_ALLCOORDS: return 3 * s->R + 2 * s->B;
+    default: return 0;
+  }
+}
+int64_t rr_launch_count(const rr_sim *s) { return s ? s->launches : 0; }
+int64_t rr_state_bytes_per_env(const rr_sim *s) { return s ? (int64_t)s->NF * 8 + (int64_t)s->NI * 4 : 0; }
+
+int rr_reset(rr_sim *s, const uint8_t *mask_dev, void *stream) {
+  if (!s) return fail(RR_E_INVALID, "null handle");
+  CK(cudaSetDevice(s->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_PRESET(s, (k_reset<NH, NG, NP, NN><<<grid_for(s->N), kBlock, 0, st>>>(s->k, s->sf, s->si, s->N, mask_dev)));
+  s->launches++;
+  CK(cudaGetLastError());
+  return RR_OK;
+}
+
+int rr_observe(rr_sim *s, void *obs_h, void *obs_g, void *stream) {
+  if (!s) return fail(RR_E_INVALID, "null handle");
+  if (rr_obs_dim(s) == 0) return RR_OK;
+  CK(cudaSetDevice(s->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (s->cfg.out_f64)
+    DISPATCH_PRESET(s, (k_observe<NH, NG, NP, NN, double><<<grid_for(s->N), kBlock, 0, st>>>(s->k, s->sf, s->si, s->N, obs_h, obs_g)));
+  else
+    DISPATCH_PRESET(s, (k_observe<NH, NG, NP, NN, float><<<grid_for(s->N), kBlock, 0, st>>>(s->k, s->sf, s->si, s->N, obs_h, obs_g)));
+  s->launches++;
+  CK(cudaGetLastError());
+  return RR_OK;
+}
+
+static int check_actions(const rr_sim *s, int32_t n_actions, int32_t k_steps) {
+  if (k_steps <= 0) return fail(RR_E_INVALID, "k_steps must be positive");
+  if (n_actions < 0) return fail(RR_E_INVALID, "n_actions must be >= 0");
+  // RR_EnvBase.py:621-622 / :270-271: more commands than robots (engines) raises
+  if (s->cfg.discrete && n_actions > s->R)
+    return fail(RR_E_INVALID, std::to_string(n_actions) + " commands but only " + std::to_string(s->R) + " robots.");
+  if (!s->cfg.discrete && (n_actions > 2 * s->R || (n_actions & 1)))
+    return fail(RR_E_INVALID, std::to_string(n_actions) + " commands but only " + std::to_string(2 * s->R) + " robot engines.");
+  return RR_OK;
+}
+
+int rr_step(rr_sim *s, const void *actions, int32_t n_actions, int32_t k_steps, void *obs_h, void *obs_g, void *rew,
+            uint8_t *done, void *stream) {
+  if (!s) return fail(RR_E_INVALID, "null handle");
+  int rc = check_actions(s, n_actions, k_steps);
+  if (rc) return rc;
+  if (n_actions > 0 && !actions) return fail(RR_E_INVALID, "actions is null");
+  CK(cudaSetDevice(s->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  Consts k = s->k;
+  k.n_actions = n_actions;
+  StepArgs a{s->sf, s->si, s->stats, actions, obs_h, obs_g, rew, done, s->N, k_steps};
+  if (s->cfg.out_f64)
+    DISPATCH_PRESET(s, (k_step<NH, NG, NP, NN, double><<<grid_for(s->N), kBlock, 0, st>>>(k, a)));
+  else
+    DISPATCH_PRESET(s, (k_step<NH, NG, NP, NN, float><<<grid_for(s->N), kBlock, 0, st>>>(k, a)));
+  s->launches++;
+  CK(cudaGetLastError());
+  return RR_OK;
+}
+
+static int ensure(void **p, size_t *cap, size_t need) {
+  if (need <= *cap) return RR_OK;
+  cudaFree(*p);
+  *p = nullptr; *cap = 0;
+  if (cudaMalloc(p, need) != cudaSuccess) { cudaGetLastError(); return fail(RR_E_NOMEM, "device staging allocation failed"); }
+  *cap = need;
+  return RR_OK;
+}
+
+int rr_step_host(rr_sim *s, const void *actions, int32_t n_actions, int32_t k_steps, void *obs_h, void *obs_g, void *rew,
+                 uint8_t *done, void *stream) {
+  if (!s) return fail(RR_E_INVALID, "null handle");
+  int rc = check_actions(s, n_actions, k_steps);
+  if (rc) return rc;
+  CK(cudaSetDevice(s->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t osz = s->cfg.out_f64 ? 8 : 4;
+  const size_t rows = (size_t)k_steps * (size_t)s->N;
+  const size_t act_b = rows * n_actions * (s->cfg.discrete ? 1 : 4);
+  const size_t obs_b = rows * rr_obs_dim(s) * osz, rew_b = rows * 2 * osz, done_b = rows;
+  if ((rc = ensure(&s->d_act, &s->cap_act, act_b ? act_b : 1))) return rc;
+  if ((rc = ensure(&s->d_obs_h, &s->cap_obs_h, obs_b ? obs_b : 1))) return rc;
+  if ((rc = ensure(&s->d_obs_g, &s->cap_obs_g, obs_b ? obs_b : 1))) return rc;
+  if ((rc = ensure(&s->d_rew, &s->cap_rew, rew_b))) return rc;
+  if ((rc = ensure((void **)&s->d_done, &s->cap_done, done_b))) return rc;
+  if (act_b) CK(cudaMemcpyAsync(s->d_act, actions, act_b, cudaMemcpyHostToDevice, st));
+  rc = rr_step(s, s->d_act, n_actions, k_steps, obs_h ? s->d_obs_h : nullptr, obs_g ? s->d_obs_g : nullptr,
+               rew ? s->d_rew : nullptr, done ? s->d_done : nullptr, stream);
+  if (rc) return rc;
+  if (obs_h && obs_b) CK(cudaMemcpyAsync(obs_h, s->d_obs_h, obs_b, cudaMemcpyDeviceToHost, st));
+  if (obs_g && obs_b) CK(cudaMemcpyAsync(obs_g, s->d_obs_g, obs_b, cudaMemcpyDeviceToHost, st));
+  if (rew) CK(cudaMemcpyAsync(rew, s->d_rew, rew_b, cudaMemcpyDeviceToHost, st));
+  if (done) CK(cudaMemcpyAsync(done, s->d_done, done_b, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return RR_OK;
+}
+
+int rr_set_state(rr_sim *s, const double *rob, const double *rhist, const int32_t *rflag, const double *ball,
+                 const int32_t *step) {
+  if (!s || !rob || !rhist || !rflag || !ball || !step) return fail(RR_E_INVALID, "null argument");
+  CK(cudaSetDevice(s->device));
+  CK(cudaDeviceSynchronize());
+  const int64_t N = s->N;
+  const int R = s->R, B = s->B;
+  std::vector<double> sf((size_t)s->NF * N);
+  std::vector<int32_t> si((size_t)s->NI * N);
+  CK(cudaMemcpy(si.data(), s->si, sizeof(int32_t) * si.size(), cudaMemcpyDeviceToHost));  // keep episode counters
+  for (int64_t i = 0; i < N; i++) {
+    int f = 0;
+    for (int r = 0; r < R; r++) {
+      const double *p = rob + (i * R + r) * 7;
+      for (int q = 0; q < 7; q++) sf[(size_t)(f + q) * N + i] = p[q];
+      const double *h = rhist + (i * R + r) * 3;
+      for (int q = 0; q < 3; q++) sf[(size_t)(f + 7 + q) * N + i] = h[q];
+      f += 10;
+      const int32_t *g = rflag + (i * R + r) * 3;
+      si[(size_t)r * N + i] = (g[0] & 0xff) | ((g[1] & 0xff) << 8) | ((g[2] ? 1 : 0) << 16);
+    }
+    for (int b = 0; b < B; b++) {
+      const double *p = ball + (i * B + b) * 8;
+      for (int q = 0; q < 8; q++) sf[(size_t)(f + q) * N + i] = p[q];
+      f += 8;
+    }
+    sf[(size_t)(f + 0) * N + i] = 0.0; sf[(size_t)(f + 1) * N + i] = 0.0;
+    si[(size_t)(R + 0) * N + i] = step[i];
+    si[(size_t)(R + 2) * N + i] = 0;
+    si[(size_t)(R + 3) * N + i] = 0;
+  }
+  CK(cudaMemcpy(s->sf, sf.data(), sizeof(double) * sf.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(s->si, si.data(), sizeof(int32_t) * si.size(), cudaMemcpyHostToDevice));
+  return RR_OK;
+}
+
+int rr_get_state(rr_sim *s, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step) {
+  if (!s || !rob || !rhist || !rflag || !ball || !step) return fail(RR_E_INVALID, "null argument");
+  CK(cudaSetDevice(s->device));
+  CK(cudaDeviceSynchronize());
+  const int64_t N = s->N;
+  const int R = s->R, B = s->B;
+  std::vector<double> sf((size_t)s->NF * N);
+  std::vector<int32_t> si((size_t)s->NI * N);
+  CK(cudaMemcpy(sf.data(), s->sf, sizeof(double) * sf.size(), cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(si.data(), s->si, sizeof(int32_t) * si.size(), cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < N; i++) {
+    int f = 0;
+    for (int r = 0; r < R; r++) {
+      double *p = rob + (i * R + r) * 7;
+      for (int q = 0; q < 7; q++) p[q] = sf[(size_t)(f + q) * N + i];
+      int32_t pk = si[(size_t)r * N + i];
+      int32_t *g = rflag + (i * R + r) * 3;
+      g[0] = (int8_t)(pk & 0xff); g[1] = (int8_t)((pk >> 8) & 0xff); g[2] = (pk >> 16) & 1;
+      double *h = rhist + (i * R + r) * 3;
+      for (int q = 0; q < 3; q++) h[q] = g[2] ? sf[(size_t)(f + 7 + q) * N + i] : 0.0;
+      f += 10;
+    }
+    for (int b = 0; b < B; b++) {
+      double *p = ball + (i * B + b) * 8;
+      for (int q = 0; q < 8; q++) p[q] = sf[(size_t)(f + q) * N + i];
+      f += 8;
+    }
+    step[i] = si[(size_t)(R + 0) * N + i];
+  }
+  return RR_OK;
+}
+
+int rr_error_mask(rr_sim *s, uint32_t *err_host, int32_t clear) {
+  if (!s || !err_host) return fail(RR_E_INVALID, "null argument");
+  CK(cudaSetDevice(s->device));
+  CK(cudaDeviceSynchronize());
+  int32_t *p = s->si + (size_t)(s->R + 2) * s->N;
+  CK(cudaMemcpy(err_host, p, sizeof(uint32_t) * s->N, cudaMemcpyDeviceToHost));
+  if (clear) CK(cudaMemset(p, 0, sizeof(uint32_t) * s->N));
+  return RR_OK;
+}
+
+int rr_last_naughty(rr_sim *s, int32_t *count_host) {
+  if (!s || !count_host) return fail(RR_E_INVALID, "null argument");
+  CK(cudaSetDevice(s->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(count_host, s->si + (size_t)(s->R + 3) * s->N, sizeof(int32_t) * s->N, cudaMemcpyDeviceToHost));
+  return RR_OK;
+}
+
+int rr_get_stats(rr_sim *s, double *stats_host) {
+  if (!s || !stats_host) return fail(RR_E_INVALID, "null argument");
+  CK(cudaSetDevice(s->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(stats_host, s->stats, sizeof(double) * RR_NUM_STATS, cudaMemcpyDeviceToHost));
+  return RR_OK;
+}
+
+int rr_stats_device_ptr(rr_sim *s, double **p) {
+  if (!s || !p) return fail(RR_E_INVALID, "null argument");
+  *p = s->stats;
+  return RR_OK;
+}
+
+int rr_clear_stats(rr_sim *s, void *stream) {
+  if (!s) return fail(RR_E_INVALID, "null handle");
+  CK(cudaSetDevice(s->device));
+  CK(cudaMemsetAsync(s->stats, 0, sizeof(double) * RR_NUM_STATS, (cudaStream_t)stream));
+  return RR_OK;
+}
+
+int rr_set_stats_buffer(rr_sim *s, double *stats_dev) {
+  if (!s) return fail(RR_E_INVALID, "null handle");
+  s->stats = stats_dev ? stats_dev : s->own_stats;
+  return RR_OK;
+}

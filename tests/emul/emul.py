@@ -1,0 +1,85 @@
+"""ctypes binding of tests/emul/librr_emul.so: the device simulator source compiled for the HOST.
+
+TEST INFRASTRUCTURE ONLY (CPU-side verification of the kernel logic); see rr_emul.cu.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from roborugby_b200._lib import Config, ABI_VERSION
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(os.path.dirname(_HERE))
+_LIB = os.path.join(_HERE, "librr_emul.so")
+_SRCS = [os.path.join(_HERE, "rr_emul.cu"), os.path.join(_ROOT, "roborugby_b200", "csrc", "rr_sim.cuh"),
+         os.path.join(_ROOT, "include", "rr_b200.h")]
+
+
+def build(force=False):
+    if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(p) for p in _SRCS):
+        subprocess.check_call([
+            "nvcc", "-O2", "-std=c++17", "--fmad=false", "-Wno-deprecated-gpu-targets",
+            "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-builtin", "-shared", "-o", _LIB, _SRCS[0]])
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB)
+        vp = C.c_void_p
+        L.emul_step.argtypes = [C.POINTER(Config), vp, vp, vp, vp, vp, vp, C.c_int, vp, vp, vp, vp, vp]
+        L.emul_step.restype = C.c_uint
+        L.emul_reset.argtypes = [C.POINTER(Config), vp, vp, vp, vp, vp, C.c_uint64, C.c_uint32, C.c_int]
+        L.emul_reset.restype = C.c_uint
+        L.emul_observe.argtypes = [C.POINTER(Config), vp, vp, vp, vp, vp, C.c_int, vp]
+        L.emul_observe.restype = C.c_uint
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class EmulEnv:
+    """One env advanced by the host build of the CUDA simulator source."""
+
+    def __init__(self, cfg, R, B, obs_dim):
+        self.cfg, self.R, self.B, self.obs_dim = cfg, R, B, obs_dim
+        self.rob = np.zeros((R, 7)); self.rhist = np.zeros((R, 3)); self.rflag = np.zeros((R, 3), np.int32)
+        self.ball = np.zeros((B, 8)); self.stepc = np.zeros(1, np.int32)
+
+    def set_state(self, st):
+        self.rob[...] = st["rob"]; self.rhist[...] = st["rhist"]; self.rflag[...] = st["rflag"]
+        self.ball[...] = st["ball"]; self.stepc[0] = st["step"]
+
+    def get_state(self):
+        return dict(rob=self.rob.copy(), rhist=self.rhist.copy(), rflag=self.rflag.copy(), ball=self.ball.copy(),
+                    step=np.int32(self.stepc[0]))
+
+    def step(self, actions):
+        a = np.ascontiguousarray(np.asarray(actions, np.float64).reshape(-1))
+        d = max(self.obs_dim, 1)
+        oh = np.full(d, np.nan); og = np.full(d, np.nan); rew = np.zeros(2)
+        done = np.zeros(1, np.int32); ng = np.zeros(1, np.int32)
+        err = lib().emul_step(C.byref(self.cfg), _p(self.rob), _p(self.rhist), _p(self.rflag), _p(self.ball),
+                              _p(self.stepc), _p(a), a.size, _p(oh), _p(og), _p(rew), _p(done), _p(ng))
+        return dict(obs_h=oh[:self.obs_dim], obs_g=og[:self.obs_dim], rew=rew, done=int(done[0]), naughty=int(ng[0]),
+                    err=int(err))
+
+    def reset(self, env_index, episode, construct=False):
+        return lib().emul_reset(C.byref(self.cfg), _p(self.rob), _p(self.rhist), _p(self.rflag), _p(self.ball),
+                                _p(self.stepc), int(env_index), int(episode), int(construct))
+
+    def observe(self, team):
+        o = np.full(max(self.obs_dim, 1), np.nan)
+        lib().emul_observe(C.byref(self.cfg), _p(self.rob), _p(self.rhist), _p(self.rflag), _p(self.ball),
+                           _p(self.stepc), int(team), _p(o))
+        return o[:self.obs_dim]

@@ -1,0 +1,125 @@
+// rr_emul.cu — HOST execution of the device simulator source (roborugby_b200/csrc/rr_sim.cuh).
+//
+// TEST INFRASTRUCTURE ONLY.  The product library (librr_b200.so) contains GPU code alone; this
+// file builds a separate, test-only library in which the same __host__ __device__ functions are
+// compiled for the CPU, so that the CPU-only test tier (-m "not gpu") can check the restructured
+// kernel logic against the oracle without a GPU.  Nothing under roborugby_b200/ loads it.
+#include <cstring>
+
+#include "../../roborugby_b200/csrc/rr_sim.cuh"
+
+using namespace rr;
+
+template <int NH, int NG, int NP, int NN>
+static void load(Env<NH, NG, NP, NN> &e, const Consts &k, const double *rob, const double *rhist, const int32_t *rflag,
+                 const double *ball, int32_t step) {
+  using E = Env<NH, NG, NP, NN>;
+  e.hvalid = 0;
+  for (int r = 0; r < E::R; r++) {
+    const double *p = rob + 7 * r;
+    e.rcx[r] = p[0]; e.rcy[r] = p[1]; e.rl[r] = p[2]; e.rr[r] = p[3]; e.rt[r] = p[4]; e.rb[r] = p[5]; e.rrot[r] = p[6];
+    e.hx[r] = rhist[3 * r]; e.hy[r] = rhist[3 * r + 1]; e.hrot[r] = rhist[3 * r + 2];
+    e.thl[r] = rflag[3 * r]; e.thr[r] = rflag[3 * r + 1];
+    if (rflag[3 * r + 2]) e.hvalid |= 1u << r;
+    robot_refresh_corners(e, k, r);
+  }
+  for (int b = 0; b < E::B; b++) {
+    const double *p = ball + 8 * b;
+    e.bcx[b] = p[0]; e.bcy[b] = p[1]; e.bl[b] = p[2]; e.br[b] = p[3]; e.bt[b] = p[4]; e.bb[b] = p[5];
+    e.bvx[b] = p[6]; e.bvy[b] = p[7];
+  }
+  e.step = step; e.err = 0; e.episode = 0; e.ret_h = e.ret_g = 0;
+}
+
+template <int NH, int NG, int NP, int NN>
+static void store(const Env<NH, NG, NP, NN> &e, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step) {
+  using E = Env<NH, NG, NP, NN>;
+  for (int r = 0; r < E::R; r++) {
+    double *p = rob + 7 * r;
+    p[0] = e.rcx[r]; p[1] = e.rcy[r]; p[2] = e.rl[r]; p[3] = e.rr[r]; p[4] = e.rt[r]; p[5] = e.rb[r]; p[6] = e.rrot[r];
+    int v = (e.hvalid >> r) & 1;
+    rhist[3 * r] = v ? e.hx[r] : 0; rhist[3 * r + 1] = v ? e.hy[r] : 0; rhist[3 * r + 2] = v ? e.hrot[r] : 0;
+    rflag[3 * r] = e.thl[r]; rflag[3 * r + 1] = e.thr[r]; rflag[3 * r + 2] = v;
+  }
+  for (int b = 0; b < E::B; b++) {
+    double *p = ball + 8 * b;
+    p[0] = e.bcx[b]; p[1] = e.bcy[b]; p[2] = e.bl[b]; p[3] = e.br[b]; p[4] = e.bt[b]; p[5] = e.bb[b];
+    p[6] = e.bvx[b]; p[7] = e.bvy[b];
+  }
+  *step = e.step;
+}
+
+template <int NH, int NG, int NP, int NN>
+static unsigned step_t(const Consts &k, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,
+                       const double *actions, int n_actions, double *obs_h, double *obs_g, double *rew, int32_t *done,
+                       int32_t *naughty) {
+  using E = Env<NH, NG, NP, NN>;
+  E e;
+  load(e, k, rob, rhist, rflag, ball, *step);
+  int cl[E::R], cr[E::R], n_cmd;
+  if (k.discrete) {
+    n_cmd = n_actions;
+    for (int r = 0; r < n_cmd && r < E::R; r++) thrust_from_direction((int)actions[r], cl[r], cr[r]);
+  } else {
+    n_cmd = n_actions / 2;
+    for (int r = 0; r < n_cmd && r < E::R; r++) {
+      cl[r] = (int)rint((double)(float)actions[2 * r]);
+      cr[r] = (int)rint((double)(float)actions[2 * r + 1]);
+    }
+  }
+  StepOut o;
+  sim_step(e, k, cl, cr, n_cmd, o);
+  unsigned oerr = 0;
+  if (obs_h) observe(e, k, 1, obs_h, oerr);
+  if (obs_g) observe(e, k, -1, obs_g, oerr);
+  rew[0] = o.rew_h; rew[1] = o.rew_g;
+  *done = o.done;
+  *naughty = rr_popc(o.naughty);
+  store(e, rob, rhist, rflag, ball, step);
+  return o.step_err;
+}
+
+template <int NH, int NG, int NP, int NN>
+static unsigned reset_t(const Consts &k, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,
+                        uint64_t env, uint32_t episode, int construct) {
+  Env<NH, NG, NP, NN> e;
+  if (construct) construct_env(e);
+  else load(e, k, rob, rhist, rflag, ball, *step);
+  e.episode = episode;
+  e.err = 0;
+  reset_env(e, k, env);
+  store(e, rob, rhist, rflag, ball, step);
+  return e.err;
+}
+
+extern "C" {
+
+unsigned emul_step(const rr_config *cfg, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,
+                   const double *actions, int n_actions, double *obs_h, double *obs_g, double *rew, int32_t *done,
+                   int32_t *naughty) {
+  Consts k = make_consts(*cfg);
+  k.n_actions = n_actions;
+  if (cfg->preset == RR_PRESET_GAME)
+    return step_t<2, 2, 4, 4>(k, rob, rhist, rflag, ball, step, actions, n_actions, obs_h, obs_g, rew, done, naughty);
+  return step_t<1, 0, 1, 0>(k, rob, rhist, rflag, ball, step, actions, n_actions, obs_h, obs_g, rew, done, naughty);
+}
+
+unsigned emul_reset(const rr_config *cfg, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,
+                    uint64_t env, uint32_t episode, int construct) {
+  Consts k = make_consts(*cfg);
+  if (cfg->preset == RR_PRESET_GAME) return reset_t<2, 2, 4, 4>(k, rob, rhist, rflag, ball, step, env, episode, construct);
+  return reset_t<1, 0, 1, 0>(k, rob, rhist, rflag, ball, step, env, episode, construct);
+}
+
+unsigned emul_observe(const rr_config *cfg, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,
+                      int team, double *obs) {
+  Consts k = make_consts(*cfg);
+  unsigned err = 0;
+  if (cfg->preset == RR_PRESET_GAME) {
+    Env<2, 2, 4, 4> e; load(e, k, rob, rhist, rflag, ball, *step); observe(e, k, team, obs, err);
+  } else {
+    Env<1, 0, 1, 0> e; load(e, k, rob, rhist, rflag, ball, *step); observe(e, k, team, obs, err);
+  }
+  return err;
+}
+}

@@ -1,0 +1,61 @@
+"""The C-ABI library loads on a CPU-only box and exports every symbol include/rr_b200.h declares."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "rr_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(rr_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_expected_surface():
+    syms = _declared_symbols()
+    for s in ("rr_create", "rr_destroy", "rr_reset", "rr_step", "rr_step_host", "rr_observe", "rr_get_state",
+              "rr_set_state", "rr_get_stats", "rr_error_mask", "rr_last_error", "rr_default_config"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol():
+    from roborugby_b200 import _lib
+    assert os.path.exists(_lib.LIB_PATH), "build first: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    missing = [s for s in _declared_symbols() if not hasattr(lib, s)]
+    assert not missing, missing
+    # the ctypes table covers the whole header, nothing more
+    assert sorted(_lib.SIGNATURES) == _declared_symbols()
+
+
+def test_default_config_env_ids():
+    from roborugby_b200 import _lib
+    c = _lib.default_config(_lib.PRESET_GAME, "RoboRugbySimpleDuel-v2")
+    assert (c.reward_mask, c.observer, c.discrete) == (7, _lib.OBS_BASIC_LIDAR, 1)
+    c = _lib.default_config(_lib.PRESET_TRAIN, "RoboRugbySimpleDuel-v3")
+    assert (c.reward_mask, c.observer, c.discrete) == (7, _lib.OBS_LIDAR6_V2, 1)
+    c = _lib.default_config(_lib.PRESET_GAME, "RoboRugbySimple-v0")
+    assert (c.reward_mask, c.observer) == (1, _lib.OBS_BASIC_LIDAR)
+    c = _lib.default_config(_lib.PRESET_GAME, "RoboRugby-v0")
+    assert (c.reward_mask, c.observer, c.discrete) == (0, _lib.OBS_NONE, 0)
+    with pytest.raises(_lib.RRError):
+        _lib.default_config(_lib.PRESET_GAME, "NoSuchEnv-v0")
+
+
+def test_create_fails_loudly_without_gpu():
+    """No CPU fallback: on a box without a CUDA device rr_create must fail, not degrade."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from roborugby_b200 import _lib
+    cfg = _lib.default_config(_lib.PRESET_TRAIN, "RoboRugbySimpleDuel-v2")
+    h = ctypes.c_void_p()
+    rc = _lib.load().rr_create(ctypes.byref(cfg), 8, 0, ctypes.byref(h))
+    assert rc != 0 and not h.value
+    assert b"no usable CUDA device" in _lib.load().rr_last_error()
+    import roborugby_b200
+    with pytest.raises(RuntimeError):
+        roborugby_b200.RoboRugbyVecEnv("RoboRugbySimpleDuel-v2", 8)

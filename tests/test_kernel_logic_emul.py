@@ -1,0 +1,121 @@
+"""CPU tier: the CUDA simulator SOURCE (roborugby_b200/csrc/rr_sim.cuh), compiled for the host by
+tests/emul, against (a) the reference's golden vectors and (b) the oracle.
+
+This checks the restructured kernel logic (flat state, collapsed history ring, culled pair tests,
+predicated drive modes, in-kernel Philox reset) on a box without a GPU.  The GPU tier
+(test_parity_gpu.py) repeats the same comparisons through the C ABI on a B200.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_files
+from golden_util import actions_at, parse_name, state_at
+from parity_util import compare_record
+
+FILES = [f for f in golden_files("*.npz") if parse_name(f)[2] in ("random", "chase", "sticky", "inject")]
+
+
+def _make(path):
+    from emul.emul import EmulEnv
+    from roborugby_b200 import _lib
+    preset, env_id, _ = parse_name(path)
+    d = np.load(path)
+    cfg = _lib.default_config(_lib.PRESET_GAME if preset == "GAME" else _lib.PRESET_TRAIN, env_id)
+    cfg.time_limit = 0
+    cfg.auto_reset = 0
+    cfg.strict_reset = 1
+    R, B, D = d["rob"].shape[2], d["ball"].shape[2], d["obs_h"].shape[2]
+    return d, cfg, EmulEnv(cfg, R, B, D), preset, env_id
+
+
+@pytest.mark.parametrize("path", FILES, ids=[p.split("/")[-1] for p in FILES])
+def test_kernel_source_matches_reference_golden(path):
+    d, cfg, env, preset, env_id = _make(path)
+    n, T = d["act"].shape[:2]
+    bad, exact, worst, total = [], 0, 0.0, 0
+    for i in range(n):
+        for t in range(T):
+            env.set_state(state_at(d, i, t))
+            out = env.step(actions_at(d, i, t))
+            total += 1
+            if d["exc"][i, t]:  # the reference raised: only the error flag is comparable
+                if out["err"] == 0:
+                    bad.append((i, t, "no error flag"))
+                else:
+                    exact += 1
+                continue
+            if out["err"]:
+                bad.append((i, t, f"spurious err {out['err']}"))
+                continue
+            want = dict(obs_h=d["obs_h"][i, t], obs_g=d["obs_g"][i, t], rew=d["rew"][i, t], done=d["done"][i, t],
+                        naughty=d["naughty"][i, t])
+            ok, ex, w, why = compare_record(env.get_state(), out, state_at(d, i, t + 1), want)
+            worst = max(worst, w)
+            exact += ex
+            if not ok:
+                bad.append((i, t, why, w))
+    assert not bad, f"{len(bad)}/{total} records out of tolerance: {bad[:5]}"
+    assert exact >= 0.6 * total, f"only {exact}/{total} bit-identical"
+    print(f"{path.split('/')[-1]}: {total} records, {exact} bit-identical, max abs err {worst:.3e}")
+
+
+@pytest.mark.parametrize("path", FILES[:6], ids=[p.split("/")[-1] for p in FILES[:6]])
+def test_kernel_source_matches_oracle_trajectories(oracle, path):
+    """Multi-step: both sides run the whole trajectory from the first state only."""
+    d, cfg, env, preset, env_id = _make(path)
+    n, T = d["act"].shape[:2]
+    oracle.scratch_mode(1)
+    try:
+        o = oracle.OracleEnv(preset, env_id)
+        for i in range(n):
+            env.set_state(state_at(d, i, 0)); o.set_state(state_at(d, i, 0))
+            for t in range(T):
+                if d["restart"][i, t]:
+                    env.set_state(state_at(d, i, t)); o.set_state(state_at(d, i, t))
+                a = actions_at(d, i, t)
+                got, want = env.step(a), o.step(a)
+                assert (got["err"] != 0) == (want["err"] != 0), (i, t)
+                if want["err"]:
+                    continue
+                ok, _, w, why = compare_record(env.get_state(), got, o.get_state(), want)
+                assert ok, (i, t, why, w)
+    finally:
+        oracle.scratch_mode(0)
+
+
+@pytest.mark.parametrize("preset", ["GAME", "TRAIN"])
+def test_philox_reset_matches_oracle(oracle, preset):
+    """In-kernel reset: same Philox stream, same placement decisions, bit-identical state."""
+    from emul.emul import EmulEnv
+    from roborugby_b200 import _lib
+    env_id = "RoboRugbySimpleDuel-v2"
+    cfg = _lib.default_config(_lib.PRESET_GAME if preset == "GAME" else _lib.PRESET_TRAIN, env_id)
+    cfg.seed = 0x1234ABCD5678
+    cfg.strict_reset = 1
+    o = oracle.OracleEnv(preset, env_id)
+    env = EmulEnv(cfg, o.R, o.B, o.obs_dim)
+    for env_index in (0, 1, 77, 2 ** 33 + 5):
+        o2 = oracle.OracleEnv(preset, env_id)
+        env.reset(env_index, 0, construct=True)
+        o2.reset_philox(cfg.seed, env_index, 0)
+        for episode in (1, 2, 3):
+            a, b = env.get_state(), o2.get_state()
+            for k in ("rob", "ball", "rflag", "step"):
+                assert np.array_equal(a[k], b[k]), (env_index, episode, k)
+            env.reset(env_index, episode)
+            o2.reset_philox(cfg.seed, env_index, episode)
+        # reset placement invariants (RR_EnvBase.py:155-200)
+        st = env.get_state()
+        W = 800 if preset == "GAME" else 600
+        assert np.all(st["rob"][:, 0] >= 80) and np.all(st["rob"][:, 0] <= W - 80)
+        assert np.all(st["rob"][:, 1] >= 40) and np.all(st["rob"][:, 1] <= W - 40)
+        assert np.all(st["ball"][:, 0] >= 40) and np.all(st["ball"][:, 0] <= W - 40)
+        assert np.all(st["ball"][:, 6:] == 0) and st["step"] == 0
+
+
+def test_philox_known_answer(oracle):
+    """Philox4x32-10 known-answer vectors (Random123 kat_vectors): zeros, and the pi/e pattern."""
+    assert oracle.philox4x32([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert oracle.philox4x32([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert oracle.philox4x32([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]

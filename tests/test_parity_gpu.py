@@ -1,0 +1,287 @@
+"""GPU tier (B200): the CUDA kernels, called through the C ABI, against the reference's golden
+vectors, against the CPU oracle on seeded inputs, and through size-independent properties at
+BASELINE.json's full batch sizes.  /root/reference is never read here."""
+import numpy as np
+import pytest
+
+from conftest import golden_files
+from golden_util import STATE_KEYS, parse_name
+from parity_util import compare_record
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+FILES = [f for f in golden_files("*.npz") if parse_name(f)[2] in ("random", "chase", "sticky", "inject")]
+V2 = "RoboRugbySimpleDuel-v2"
+
+
+def _venv(env_id, n, preset, **kw):
+    from roborugby_b200.vec_env import RoboRugbyVecEnv
+    kw.setdefault("time_limit", False)
+    kw.setdefault("auto_reset", False)
+    kw.setdefault("out_dtype", torch.float64)
+    kw.setdefault("strict_reset", True)
+    return RoboRugbyVecEnv(env_id, n, preset=preset, device="cuda:0", **kw)
+
+
+@pytest.mark.parametrize("path", FILES, ids=[p.split("/")[-1] for p in FILES])
+def test_gpu_step_matches_reference_golden(path):
+    """Every golden record is injected into its own env; ONE launch per action-count group."""
+    preset, env_id, _ = parse_name(path)
+    d = np.load(path)
+    n, T = d["act"].shape[:2]
+    flat = {k: d[k][:, :-1].reshape((n * T,) + d[k].shape[2:]) for k in STATE_KEYS}
+    after = {k: d[k][:, 1:].reshape((n * T,) + d[k].shape[2:]) for k in STATE_KEYS}
+    act = d["act"].reshape(n * T, -1)
+    n_act = (~np.isnan(act)).sum(1)
+    outs = {k: d[k].reshape((n * T,) + d[k].shape[2:]) for k in ("obs_h", "obs_g", "rew", "done", "naughty", "exc")}
+    discrete = env_id != "RoboRugby-v0"
+    bad, exact, worst = [], 0, 0.0
+    for A in np.unique(n_act):
+        idx = np.nonzero(n_act == A)[0]
+        env = _venv(env_id, len(idx), preset)
+        env.set_state({k: flat[k][idx] for k in STATE_KEYS})
+        a = act[idx, :A]
+        a_t = torch.as_tensor(a.astype(np.uint8 if discrete else np.float32)).reshape(1, len(idx), A).cuda()
+        obs_h, obs_g, rew, done = env.step_k(a_t, 1)
+        torch.cuda.synchronize()
+        st = env.get_state()
+        err = env.error_mask()
+        ng = env.last_naughty()
+        obs_h, obs_g, rew, done = (x[0].cpu().numpy() for x in (obs_h, obs_g, rew, done))
+        for j, r in enumerate(idx):
+            if outs["exc"][r]:
+                if err[j] == 0:
+                    bad.append((int(r), "no error flag"))
+                else:
+                    exact += 1
+                continue
+            if err[j]:
+                bad.append((int(r), f"spurious err {err[j]}"))
+                continue
+            got_out = dict(obs_h=obs_h[j], obs_g=obs_g[j], rew=rew[j], done=done[j], naughty=ng[j])
+            want_out = {k: outs[k][r] for k in ("obs_h", "obs_g", "rew", "done", "naughty")}
+            ok, ex, w, why = compare_record({k: st[k][j] for k in STATE_KEYS}, got_out,
+                                            {k: after[k][r] for k in STATE_KEYS}, want_out)
+            worst = max(worst, w)
+            exact += ex
+            if not ok:
+                bad.append((int(r), why, w))
+        env.close()
+    print(f"{path.split('/')[-1]}: {n * T} records, {exact} bit-identical, max abs err {worst:.3e}")
+    assert not bad, f"{len(bad)}/{n * T} records out of tolerance: {bad[:5]}"
+
+
+def _golden_states(preset, limit):
+    """A pool of realistic (contact-rich) states harvested from the golden files."""
+    pool = {k: [] for k in STATE_KEYS}
+    for f in FILES:
+        p, env_id, kind = parse_name(f)
+        if p != preset or env_id != V2:
+            continue
+        d = np.load(f)
+        ok = d["exc"].sum(1) == 0
+        for k in STATE_KEYS:
+            x = d[k][ok][:, :-1]
+            pool[k].append(x.reshape((-1,) + x.shape[2:]))
+    pool = {k: np.concatenate(v)[:limit] for k, v in pool.items()}
+    pool["step"] = np.minimum(pool["step"], 100).astype(np.int32)
+    return pool
+
+
+@pytest.mark.parametrize("preset,K", [("TRAIN", 16), ("GAME", 8)])
+def test_gpu_fused_multistep_matches_oracle(oracle, preset, K):
+    """K fused steps in one launch vs K oracle steps, from contact-rich states, random actions."""
+    pool = _golden_states(preset, 768)
+    N = len(pool["step"])
+    env = _venv(V2, N, preset)
+    env.set_state(pool)
+    g = torch.Generator().manual_seed(1234)
+    acts = torch.randint(0, 8, (K, N, env.num_robots), generator=g, dtype=torch.uint8)
+    obs_h, obs_g, rew, done = (x.cpu().numpy() for x in env.step_k(acts.cuda(), K))
+    st = env.get_state()
+    err = env.error_mask()
+    oracle.scratch_mode(1)
+    try:
+        bad, exact, worst = [], 0, 0.0
+        o = oracle.OracleEnv(preset, V2)
+        for i in range(N):
+            o.set_state({k: pool[k][i] for k in STATE_KEYS})
+            raised = False
+            for s in range(K):
+                out = o.step(acts[s, i].numpy())
+                if out["err"]:
+                    raised = True
+                    break
+                got = dict(obs_h=obs_h[s, i], obs_g=obs_g[s, i], rew=rew[s, i], done=done[s, i], naughty=out["naughty"])
+                if s < K - 1:  # intermediate steps: outputs only
+                    ok, ex, w, why = compare_record(o.get_state(), got, o.get_state(), out)
+                else:
+                    ok, ex, w, why = compare_record({k: st[k][i] for k in STATE_KEYS}, got, o.get_state(), out)
+                    exact += ex
+                worst = max(worst, w)
+                if not ok:
+                    bad.append((i, s, why, w))
+                    break
+            if raised:
+                assert err[i] != 0, (i, "oracle raised, gpu did not")
+            else:
+                assert err[i] == 0, (i, "gpu raised, oracle did not", err[i])
+        print(f"{preset}: {N} envs x {K} fused steps, {exact} final states bit-identical, max abs err {worst:.3e}")
+        assert not bad, bad[:5]
+    finally:
+        oracle.scratch_mode(0)
+    env.close()
+
+
+@pytest.mark.parametrize("preset", ["TRAIN", "GAME"])
+def test_gpu_reset_and_autoreset_match_oracle(oracle, preset):
+    """rr_create/rr_reset placement == oracle Philox reset (bit-exact); auto-reset fires at the
+    TimeLimit step inside a fused launch and continues from the oracle's reset state."""
+    N, seed, off = 64, 99, 1000
+    env = _venv(V2, N, preset, seed=seed, env_offset=off, time_limit=True, auto_reset=True)
+    T = env.max_episode_steps
+    st = env.get_state()
+    orcs = []
+    for i in range(N):
+        o = oracle.OracleEnv(preset, V2, time_limit=True)
+        o.reset_philox(seed, off + i, 0)
+        ref = o.get_state()
+        for k in ("rob", "ball", "rflag", "step"):
+            assert np.array_equal(ref[k], st[k][i]), (i, k)
+        orcs.append(o)
+    # jump to the end of the episode
+    st["step"][:] = T - 2
+    env.set_state(st)
+    K = 4
+    g = torch.Generator().manual_seed(5)
+    acts = torch.randint(0, 8, (K, N, env.num_robots), generator=g, dtype=torch.uint8)
+    obs_h, obs_g, rew, done = (x.cpu().numpy() for x in env.step_k(acts.cuda(), K))
+    assert (done[:, :].sum(0) == 1).all() and (done[1] == 1).all(), "TimeLimit: done exactly when step == T"
+    st2 = env.get_state()
+    oracle.scratch_mode(1)
+    try:
+        for i, o in enumerate(orcs):
+            s0 = o.get_state(); s0["step"] = np.int32(T - 2); o.set_state(s0)
+            for s in range(K):
+                out = o.step(acts[s, i].numpy())
+                assert out["done"] == done[s, i]
+                if out["done"]:
+                    o.reset_philox(seed, off + i, 1)
+                    first = o.observe(1)
+                    assert np.allclose(first, obs_h[s, i], rtol=1e-9, atol=1e-9), "obs after auto-reset = first obs"
+            ref = o.get_state()
+            assert int(ref["step"]) == int(st2["step"][i]) == 2
+            for k in ("rob", "ball"):
+                assert np.allclose(ref[k], st2[k][i], rtol=1e-9, atol=1e-9), (i, k)
+    finally:
+        oracle.scratch_mode(0)
+    stats = env.get_stats()
+    assert stats["episodes"] == N and stats["steps"] == N * K and stats["length"] == N * T
+    env.close()
+
+
+def test_gpu_shard_invariance():
+    """Splitting the batch over ranks (env_offset) does not change any env's trajectory."""
+    K, N = 6, 512
+    g = torch.Generator().manual_seed(8)
+    acts = torch.randint(0, 8, (K, N, 4), generator=g, dtype=torch.uint8).cuda()
+    whole = _venv(V2, N, "GAME", seed=3, auto_reset=True, time_limit=True)
+    whole.step_k(acts, K)
+    a = whole.get_state()
+    halves = []
+    for r in range(2):
+        h = _venv(V2, N // 2, "GAME", seed=3, env_offset=r * N // 2, auto_reset=True, time_limit=True)
+        h.step_k(acts[:, r * N // 2:(r + 1) * N // 2].contiguous(), K)
+        halves.append(h.get_state())
+    for k in STATE_KEYS:
+        assert np.array_equal(a[k], np.concatenate([halves[0][k], halves[1][k]])), k
+
+
+@pytest.mark.parametrize("preset,N", [("GAME", 65536), ("TRAIN", 65536)])
+def test_gpu_full_size_properties(preset, N):
+    """BASELINE config 3 size: invariants that hold for any trajectory, plus determinism."""
+    K = 16
+    results = []
+    for rep in range(2):
+        env = _venv(V2, N, preset, seed=11, auto_reset=True, time_limit=True, out_dtype=torch.float32,
+                    strict_reset=False)
+        T = env.max_episode_steps
+        st = env.get_state()
+        st["step"][::7] = T - 5  # a seventh of the envs finish inside the launch
+        env.set_state(st)
+        g = torch.Generator(device="cuda").manual_seed(2)
+        acts = torch.randint(0, 8, (K, N, env.num_robots), generator=g, dtype=torch.uint8, device="cuda")
+        obs_h, obs_g, rew, done = env.step_k(acts, K)
+        torch.cuda.synchronize()
+        s = env.get_state()
+        results.append((s, obs_h.clone(), rew.clone(), done.clone()))
+        W = env.preset.arena_width
+        assert np.isfinite(s["rob"]).all() and np.isfinite(s["ball"]).all()
+        # robots stay inside the arena (RR_Robot.py:187-203), rotation normalised (MyUtils.py:279)
+        assert (s["rob"][:, :, 2] >= 0).all() and (s["rob"][:, :, 3] <= W).all()
+        assert (s["rob"][:, :, 4] > 0).all() and (s["rob"][:, :, 5] < W).all()
+        assert (s["rob"][:, :, 6] >= 0).all() and (s["rob"][:, :, 6] < 360).all()
+        # balls: centre inside the arena up to the 1-px truncation slack of collided_wall
+        assert (s["ball"][:, :, 0] > 5).all() and (s["ball"][:, :, 0] < W - 5).all()
+        # step counters: finished envs restarted, the rest advanced by K
+        fin = np.zeros(N, bool); fin[::7] = True
+        assert (s["step"][~fin] == K).all() and (s["step"][fin] == K - 5).all()
+        d = done.cpu().numpy()
+        assert (d[:, ~fin] == 0).all() and (d[4, fin] == 1).all() and (d[:, fin].sum(0) == 1).all()
+        assert (env.error_mask() == 0).all()
+        stats = env.get_stats()
+        assert stats["episodes"] == fin.sum() and stats["steps"] == N * K
+        assert torch.isfinite(rew).all() and torch.isfinite(obs_h).all()
+        env.close()
+    for k in STATE_KEYS:
+        assert np.array_equal(results[0][0][k], results[1][0][k]), "bitwise deterministic"
+    assert torch.equal(results[0][1], results[1][1]) and torch.equal(results[0][2], results[1][2])
+
+
+def test_gpu_host_buffer_entry_point_matches_device_path():
+    N, K = 2048, 4
+    g = torch.Generator().manual_seed(4)
+    acts = torch.randint(0, 8, (K, N, 4), generator=g, dtype=torch.uint8)
+    a = _venv(V2, N, "GAME", seed=5, out_dtype=torch.float32)
+    b = _venv(V2, N, "GAME", seed=5, out_dtype=torch.float32)
+    oh, og, rew, done = a.step_k(acts.cuda(), K)
+    out = b.step_host(acts.pin_memory(), K)
+    assert torch.equal(oh.cpu(), out["obs_h"]) and torch.equal(og.cpu(), out["obs_g"])
+    assert torch.equal(rew.cpu(), out["rew"]) and torch.equal(done.cpu(), out["done"])
+
+
+def test_gpu_gym_wrapper_drop_in():
+    import roborugby_b200 as rr
+    env = rr.make(V2, preset="TRAIN")
+    assert env.spec.max_episode_steps == 300 and env.action_space.n == 8 and env.observation_space.shape == (5,)
+    obs = env.reset()
+    assert obs is None  # PosBall_BasicLidar returns None without a team (RR_Observers.py:133-141)
+    obs = env.unwrapped.get_game_state(int_team=rr.TEAM_HAPPY)
+    assert obs.shape == (5,) and env.unwrapped.get_game_state(int_team=rr.TEAM_GRUMPY) is None
+    o, r, d, info = env.step([0])
+    assert o.shape == (5,) and isinstance(r, float) and d is False
+    assert info.adblGrumpyState is None and info.dblGrumpyScore == pytest.approx(-r + 0.0, abs=1e9)
+    with pytest.raises(Exception, match="commands but only 1 robots"):
+        env.step([0, 1])
+    assert env.sprHappyGoal.get_score() == 0 and not env.sprGrumpyGoal.is_destroyed()
+    done = False
+    n = 1
+    while not done:
+        o, r, done, info = env.step([2])
+        n += 1
+    assert n == 300 and info["TimeLimit.truncated"] is True
+    raw = rr.RoboRugbyEnv(V2, preset="TRAIN", time_limit=False)
+    raw.reset()
+    st = raw.get_state(); st["step"] = np.int32(300); raw.set_state(st)
+    assert raw.step([0])[2] is True
+    with pytest.raises(Exception, match="Game is over"):
+        raw.step([0])
+    env3 = rr.make("RoboRugbySimpleDuel-v3", preset="GAME")
+    assert env3.reset().shape == (11,)
+    o, r, d, info = env3.step([0, 1, 2, 3])
+    assert info.adblGrumpyState.shape == (11,)
+    full = rr.make("RoboRugby-v0", preset="GAME")
+    assert full.reset() is None and full.action_space.shape == (4,)
+    o, r, d, info = full.step([(1.0, 1.0), (0.4, -0.6)])
+    assert o is None and r == 0.0
