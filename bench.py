@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/s of the RoboRugby step()/reset() hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--preset GAME|TRAIN]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[2]): RoboRugbySimpleDuel-v2, 65 536 envs per GPU, shipped (GAME)
+constants, uniformly random discrete actions for all four robots, fused launches of 16 env-steps
+with in-kernel auto-reset.  One bench "step" = one fused launch = 65 536 x 16 env-steps per GPU.
+
+  value    whole-job env-steps/s, inputs (actions) already resident in HBM, CUDA-event timed,
+           max over ranks, L2 flushed between timed launches
+  e2e      the same launches through the HOST-buffer C-ABI entry point rr_step_host: actions copied
+           host->device and observations/rewards/done copied device->host inside the timed region
+  roofline HBM: algorithmic bytes per launch / measured kernel time vs MEASURED_PEAKS.json
+  cpu_baseline  the C oracle (port of the reference algorithm, oracle/) on the host cores, N=1 only
+
+--impl reference times the reference algorithm's CPU implementation on the host cores (the C
+oracle port; the Python reference itself cannot travel to the GPU box — its measured rate in the
+build container is recorded in DESIGN.md).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENV_ID = "RoboRugbySimpleDuel-v2"
+ENVS_PER_GPU = 65536
+FUSED = 16
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self._stop_evt, self.proc = gpu_index, [], threading.Event(), None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                if self._stop_evt.is_set():
+                    break
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference algorithm on the host cores (C oracle port)."""
+    if rank != 0:
+        return
+    from oracle import rr_oracle
+    cores = os.cpu_count() or 1
+    per_core = 1500 if args.preset == "GAME" else 40000  # ~2 s per bench step on each core
+    vals, walls = [], []
+    for it in range(args.warmup + args.steps):
+        v, wall = rr_oracle.timed_rollout(args.preset, ENV_ID, per_core, cores)
+        if it >= args.warmup:
+            vals.append(v); walls.append(wall)
+    value = sum(vals) / len(vals)
+    sample = f"{per_core} random-action env-steps per core x {cores} cores per bench step, C oracle (oracle/rr_oracle.c)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * sum(walls) / len(walls), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def workload_config(args, world):
+    return {"workload": f"{ENV_ID} {args.preset} preset, {args.envs} envs/GPU x {world} GPU, random discrete actions, "
+                        f"{args.fused} fused env-steps per launch, auto-reset (BASELINE configs[2])",
+            "env_id": ENV_ID, "preset": args.preset, "envs_per_gpu": args.envs, "fused_steps": args.fused,
+            "parallelism": f"env-shard x{world} (no data-path collective)", "l2": "flushed between timed launches"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--preset", default="GAME", choices=["GAME", "TRAIN"])
+    ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
+    ap.add_argument("--fused", type=int, default=FUSED)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    # CPU baseline first (rank 0, N=1 only), before this process touches CUDA
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import rr_oracle
+        cores = os.cpu_count() or 1
+        per_core = 3000 if args.preset == "GAME" else 80000
+        v, wall = rr_oracle.timed_rollout(args.preset, ENV_ID, per_core, cores)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{per_core} random-action env-steps per core on {cores} cores ({wall:.1f} s), "
+                                  f"C oracle port of the reference algorithm, same env id and preset"}
+
+    import torch
+    import torch.distributed as dist
+    from roborugby_b200 import shard_envs
+    from roborugby_b200.vec_env import RoboRugbyVecEnv
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    N, K = args.envs, args.fused
+    total = N * world
+    n_local, offset = shard_envs(total, rank, world)
+    env = RoboRugbyVecEnv(ENV_ID, n_local, preset=args.preset, device=dev, seed=2026, env_offset=offset,
+                          time_limit=True, auto_reset=True, out_dtype=torch.float32)
+    R, D = env.num_robots, env.obs_dim
+    g = torch.Generator(device=dev).manual_seed(1 + rank)
+    n_sets = 4  # rotate pre-generated action sets so consecutive launches differ
+    acts = [torch.randint(0, 8, (K, n_local, R), generator=g, dtype=torch.uint8, device=dev) for _ in range(n_sets)]
+    acts_host = [a.cpu().pin_memory() for a in acts]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # desynchronise episode phases so resets are spread over launches like a long-running job
+    st = env.get_state()
+    import numpy as np
+    st["step"][:] = (np.arange(n_local) * 7919) % max(env.max_episode_steps - 1, 1)
+    env.set_state(st)
+
+    for w in range(args.warmup):
+        env.step_k(acts[w % n_sets], K)
+    barrier()
+
+    # ---------------- device-resident timing (value) ----------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = env.launch_count
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for s in range(args.steps):
+        flush.fill_(s & 0xff)  # evict state/action lines from L2 (outside the timed event pair)
+        ev[s][0].record()
+        env.step_k(acts[s % n_sets], K)
+        ev[s][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = env.launch_count - launches0
+    kernel_ms = [a.elapsed_time(b) for a, b in ev]
+    my_ms = sum(kernel_ms)
+    t = torch.tensor([my_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    max_ms = float(t.item())
+    value = total * K * args.steps / (max_ms * 1e-3)
+
+    # ---------------- end-to-end through the host-buffer C-ABI entry point ----------------
+    e2e_steps = max(3, min(args.steps, 10))
+    out = env.step_host(acts_host[0], K)  # allocates pinned result buffers + device staging
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        out = env.step_host(acts_host[s % n_sets], K)
+        _ = float(out["rew"][K - 1, 0, 0])  # the caller reads the step's result on the host
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = total * K * e2e_steps / float(t.item())
+    h2d = K * n_local * R
+    d2h = K * n_local * (2 * D * 4 + 2 * 4 + 1)
+    sampler.stop()
+
+    stats = env.reduce_stats()  # the one optional collective: 64-byte all-reduce of episode statistics
+    err_envs = int((env.error_mask() != 0).sum())
+
+    if rank == 0:
+        peak, peak_src = _peaks()
+        S = env.state_bytes_per_env
+        q = 2.0 * S / K + R + 2 * D * 4 + 2 * 4 + 1  # algorithmic bytes per env-step
+        bytes_per_launch = q * n_local * K
+        avg_kernel_s = (sum(kernel_ms) / len(kernel_ms)) * 1e-3
+        achieved = bytes_per_launch / avg_kernel_s / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "bytes_per_env_step": q, "state_bytes": S,
+                         "kernel": "rr::k_step<2,2,4,4,float>" if args.preset == "GAME" else "rr::k_step<1,0,1,0,float>",
+                         "note": "path is fp64-issue bound, not HBM bound (DESIGN.md §4)"},
+            "clocks": sampler.summary(),
+            "episode_stats": {k: stats[k] for k in ("episodes", "mean_return_happy", "mean_return_grumpy", "mean_length",
+                                                    "naughty", "errors", "steps")},
+            "error_envs": err_envs,
+            "wall_s_timed_region": t_wall,
+        }
+        if cpu_baseline is not None:
+            line["cpu_baseline"] = cpu_baseline
+        print(json.dumps(line), flush=True)
+    env.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -97,6 +97,9 @@ void rro_reset_philox(rro_env *e, uint64_t seed, uint64_t env_index, uint32_t ep
 void rro_scratch_mode(int fresh);
 void rro_scratch_reset(void);
 
+void rro_set_starting_positions(rro_env *e, const double *rob3, const double *ball2);
+long rro_rollout(rro_env *e, long n_steps, uint64_t seed);
+
 /* Philox4x32-10 exposed for the RNG known-answer test. */
 void rro_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 

@@ -67,6 +67,8 @@ def lib():
         L.rro_reset_draws.restype = C.c_int
         L.rro_reset_philox.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32]
         L.rro_set_starting_positions.argtypes = [C.c_void_p, dp, dp]
+        L.rro_rollout.argtypes = [C.c_void_p, C.c_long, C.c_uint64]
+        L.rro_rollout.restype = C.c_long
         L.rro_scratch_mode.argtypes = [C.c_int]
         L.rro_scratch_reset.argtypes = []
         L.rro_philox4x32.argtypes = [C.POINTER(C.c_uint32)] * 3
@@ -140,6 +142,10 @@ class OracleEnv:
     def reset_philox(self, seed, env_index, episode):
         lib().rro_reset_philox(self._h, int(seed), int(env_index), int(episode))
 
+    def rollout(self, n_steps, seed):
+        """n_steps random-action env-steps entirely in C (timing leg of bench.py)."""
+        return int(lib().rro_rollout(self._h, int(n_steps), int(seed)))
+
     def set_starting_positions(self, rob3, ball2):
         r = np.ascontiguousarray(rob3, np.float64); b = np.ascontiguousarray(ball2, np.float64)
         lib().rro_set_starting_positions(self._h, _dp(r), _dp(b))
@@ -157,3 +163,28 @@ def philox4x32(ctr, key):
     c = (C.c_uint32 * 4)(*ctr); k = (C.c_uint32 * 2)(*key); o = (C.c_uint32 * 4)()
     lib().rro_philox4x32(c, k, o)
     return list(o)
+
+
+def _rollout_worker(args):
+    import time
+    preset, env_id, n_steps, seed = args
+    env = OracleEnv(preset, env_id, time_limit=True)
+    env.rollout(min(200, n_steps), seed)  # warm-up
+    t0 = time.perf_counter()
+    env.rollout(n_steps, seed + 1)
+    return n_steps, time.perf_counter() - t0
+
+
+def timed_rollout(preset, env_id, n_steps_per_core, cores):
+    """Random-action rollouts of the C oracle on `cores` processes; returns (env_steps/s aggregate, seconds).
+
+    Runs oracle/time_oracle.py in a child interpreter so that the caller's CUDA context (bench.py)
+    is never forked."""
+    import json
+    import sys
+    build()
+    out = subprocess.run([sys.executable, os.path.join(_HERE, "time_oracle.py"), preset, env_id,
+                          str(int(n_steps_per_core)), str(int(cores))], check=True, capture_output=True, text=True,
+                         timeout=900)
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    return d["steps_per_s"], d["wall_s"]

@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librr_b200.so")
+LIB_PATH = os.environ.get("RR_B200_LIB", os.path.join(_HERE, "librr_b200.so"))
 
 ABI_VERSION = 1
 PRESET_GAME, PRESET_TRAIN = 0, 1
