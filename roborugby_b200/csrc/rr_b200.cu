@@ -25,42 +25,63 @@
 
 namespace rr {
 
-constexpr int kBlock = 128;
-
+// Launch geometry.  One block per SM is the target: its warps are re-synchronised every physics
+// frame so that they share instruction-cache lines, and the batch is spread over all 148 SMs in one
+// wave.  The hot per-env doubles (robot rects) live in shared memory, [field][thread] with the block
+// size as stride: GAME 56 doubles x 448 threads = 196 KB; the cold ones (balls, history slots) in a
+// per-thread local array.
 template <int NH, int NG, int NP, int NN>
-struct Layout {
+struct Launch {
   static constexpr int R = NH + NG, B = NP + NN;
+  using E = Env<NH, NG, NP, NN>;
+  // largest block: bounded by 227 KB of shared memory and by 65 536 registers per SM
+  static constexpr int kMaxBlock = R > 1 ? 448 : 512;
+  static constexpr size_t smem_bytes(int block) { return sizeof(double) * E::kDoubles * (size_t)block; }
+  // HBM structure-of-arrays layout
   static constexpr int kRobotF = 10, kBallF = 8;
   static constexpr int NF = R * kRobotF + B * kBallF + 2;
   static constexpr int NI = R + 4;
 };
 
-template <int NH, int NG, int NP, int NN>
-__device__ __forceinline__ void load_env(Env<NH, NG, NP, NN> &e, const Consts &k, const double *__restrict__ sf,
+// Block size for n envs: spread over all SMs first (a multiple of one warp), then grow up to kMaxBlock.
+static inline int pick_block(int64_t n, int sms, int max_block) {
+  int64_t per_sm = (n + sms - 1) / sms;
+  int64_t b = ((per_sm + 31) / 32) * 32;
+  if (b < 32) b = 32;
+  if (b > max_block) b = max_block;
+  return (int)b;
+}
+
+extern __shared__ double rr_smem[];
+
+// HBM column -> (hot shared / cold local) fields.  Robot columns: cx,cy,l,r,t,b,rot,hx,hy,hrot.
+template <class L>
+__device__ __forceinline__ void load_env(typename L::E &e, double *cold, const Consts &k, const double *__restrict__ sf,
                                          const int32_t *__restrict__ si, int64_t N, int64_t i) {
-  using L = Layout<NH, NG, NP, NN>;
+  e.base = rr_smem + threadIdx.x;
+  e.cold = cold;
+  e.stride = (int)blockDim.x;
   int f = 0;
   e.hvalid = 0;
-#pragma unroll
+  e.thrust = 0;
+  e.masks_dirty = true;
+  e.br_near = e.bb_near = e.rr_near = e.wall_near = e.moving = 0;
+#pragma unroll 1
   for (int r = 0; r < L::R; r++) {
-    e.rcx[r] = sf[(f + 0) * N + i]; e.rcy[r] = sf[(f + 1) * N + i];
-    e.rl[r] = sf[(f + 2) * N + i];  e.rr[r] = sf[(f + 3) * N + i];
-    e.rt[r] = sf[(f + 4) * N + i];  e.rb[r] = sf[(f + 5) * N + i];
-    e.rrot[r] = sf[(f + 6) * N + i];
-    e.hx[r] = sf[(f + 7) * N + i];  e.hy[r] = sf[(f + 8) * N + i]; e.hrot[r] = sf[(f + 9) * N + i];
+#pragma unroll
+    for (int q = 0; q < 7; q++) e.rf(r, q) = sf[(f + q) * N + i];
+#pragma unroll
+    for (int q = 0; q < 3; q++) e.rc(r, q) = sf[(f + 7 + q) * N + i];
     f += L::kRobotF;
     int32_t p = si[r * N + i];
-    e.thl[r] = (int)(int8_t)(p & 0xff);
-    e.thr[r] = (int)(int8_t)((p >> 8) & 0xff);
+    e.set_thrust(r, (int)(int8_t)(p & 0xff), (int)(int8_t)((p >> 8) & 0xff));
     e.hvalid |= ((p >> 16) & 1u) << r;
     robot_refresh_corners(e, k, r);
   }
-#pragma unroll
+#pragma unroll 1
   for (int b = 0; b < L::B; b++) {
-    e.bcx[b] = sf[(f + 0) * N + i]; e.bcy[b] = sf[(f + 1) * N + i];
-    e.bl[b] = sf[(f + 2) * N + i];  e.br[b] = sf[(f + 3) * N + i];
-    e.bt[b] = sf[(f + 4) * N + i];  e.bb[b] = sf[(f + 5) * N + i];
-    e.bvx[b] = sf[(f + 6) * N + i]; e.bvy[b] = sf[(f + 7) * N + i];
+#pragma unroll
+    for (int q = 0; q < L::kBallF; q++) e.bf(b, q) = sf[(f + q) * N + i];
     f += L::kBallF;
   }
   e.ret_h = sf[(f + 0) * N + i]; e.ret_g = sf[(f + 1) * N + i];
@@ -69,27 +90,23 @@ __device__ __forceinline__ void load_env(Env<NH, NG, NP, NN> &e, const Consts &k
   e.err = (unsigned)si[(L::R + 2) * N + i];
 }
 
-template <int NH, int NG, int NP, int NN>
-__device__ __forceinline__ void store_env(const Env<NH, NG, NP, NN> &e, double *__restrict__ sf, int32_t *__restrict__ si,
+template <class L>
+__device__ __forceinline__ void store_env(const typename L::E &e, double *__restrict__ sf, int32_t *__restrict__ si,
                                           int64_t N, int64_t i, int last_naughty) {
-  using L = Layout<NH, NG, NP, NN>;
   int f = 0;
-#pragma unroll
+#pragma unroll 1
   for (int r = 0; r < L::R; r++) {
-    sf[(f + 0) * N + i] = e.rcx[r]; sf[(f + 1) * N + i] = e.rcy[r];
-    sf[(f + 2) * N + i] = e.rl[r];  sf[(f + 3) * N + i] = e.rr[r];
-    sf[(f + 4) * N + i] = e.rt[r];  sf[(f + 5) * N + i] = e.rb[r];
-    sf[(f + 6) * N + i] = e.rrot[r];
-    sf[(f + 7) * N + i] = e.hx[r];  sf[(f + 8) * N + i] = e.hy[r]; sf[(f + 9) * N + i] = e.hrot[r];
-    f += L::kRobotF;
-    si[r * N + i] = (e.thl[r] & 0xff) | ((e.thr[r] & 0xff) << 8) | (((e.hvalid >> r) & 1u) << 16);
-  }
 #pragma unroll
+    for (int q = 0; q < 7; q++) sf[(f + q) * N + i] = e.rf(r, q);
+#pragma unroll
+    for (int q = 0; q < 3; q++) sf[(f + 7 + q) * N + i] = e.rc(r, q);
+    f += L::kRobotF;
+    si[r * N + i] = (e.thl(r) & 0xff) | ((e.thr(r) & 0xff) << 8) | (((e.hvalid >> r) & 1u) << 16);
+  }
+#pragma unroll 1
   for (int b = 0; b < L::B; b++) {
-    sf[(f + 0) * N + i] = e.bcx[b]; sf[(f + 1) * N + i] = e.bcy[b];
-    sf[(f + 2) * N + i] = e.bl[b];  sf[(f + 3) * N + i] = e.br[b];
-    sf[(f + 4) * N + i] = e.bt[b];  sf[(f + 5) * N + i] = e.bb[b];
-    sf[(f + 6) * N + i] = e.bvx[b]; sf[(f + 7) * N + i] = e.bvy[b];
+#pragma unroll
+    for (int q = 0; q < L::kBallF; q++) sf[(f + q) * N + i] = e.bf(b, q);
     f += L::kBallF;
   }
   sf[(f + 0) * N + i] = e.ret_h; sf[(f + 1) * N + i] = e.ret_g;
@@ -116,49 +133,62 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-// The fused multi-step kernel: K env-steps per launch, auto-reset inside.
-template <int NH, int NG, int NP, int NN, typename OutT>
-__global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ Consts k, const __grid_constant__ StepArgs a) {
-  using E = Env<NH, NG, NP, NN>;
+// The fused multi-step kernel: K env-steps per launch, auto-reset inside.  Padding threads of the
+// last block (i >= N) run the control flow without an env so that the per-frame barrier is uniform.
+template <class L, typename OutT>
+__global__ void __launch_bounds__(L::kMaxBlock, 1) k_step(const __grid_constant__ Consts k, const __grid_constant__ StepArgs a) {
+  using E = typename L::E;
   constexpr int R = E::R;
-  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = i < a.N;
   double st[RR_NUM_STATS];
 #pragma unroll
   for (int q = 0; q < RR_NUM_STATS; q++) st[q] = 0.0;
+  E e;
+  double cold[E::kColdDoubles];
   if (live) {
-    E e;
-    load_env(e, k, a.sf, a.si, a.N, i);
-    const int dim = obs_dim_of<NH, NG, NP, NN>(k.observer);
-    const int A = k.n_actions;
-    int last_naughty = 0;
-    for (int s = 0; s < a.K; s++) {
-      const int64_t row = (int64_t)s * a.N + i;
-      int cl[R], cr[R], n_cmd;
+    load_env<L>(e, cold, k, a.sf, a.si, a.N, i);
+  } else {
+    e.base = rr_smem + threadIdx.x; e.cold = cold; e.stride = (int)blockDim.x;
+    e.err = 0; e.step = 0; e.masks_dirty = false;
+  }
+  const int dim = obs_dim_of<E>(k.observer);
+  const int A = k.n_actions;
+  int last_naughty = 0;
+#pragma unroll 1
+  for (int s = 0; s < a.K; s++) {
+    const int64_t row = (int64_t)s * a.N + i;
+    unsigned cmd = 0;
+    int n_cmd = 0;
+    if (live) {
       if (k.discrete) {
         const uint8_t *ap = (const uint8_t *)a.actions + row * A;
         n_cmd = A;
-        if (A == 4 && R >= 4) {  // one coalesced 32-bit load per env
-          uint32_t w = *(const uint32_t *)ap;
-#pragma unroll
-          for (int r = 0; r < 4 && r < R; r++) thrust_from_direction((w >> (8 * r)) & 0xff, cl[r], cr[r]);
+        uint32_t w = 0;
+        if (A == 4) {  // one coalesced 32-bit load per env
+          w = *(const uint32_t *)ap;
         } else {
+#pragma unroll 1
+          for (int r = 0; r < A; r++) w |= (uint32_t)ap[r] << (8 * r);
+        }
 #pragma unroll
-          for (int r = 0; r < R; r++)
-            if (r < A) thrust_from_direction(ap[r], cl[r], cr[r]);
+        for (int r = 0; r < R; r++) {
+          int l, rt_;
+          thrust_from_direction((w >> (8 * r)) & 0xff, l, rt_);
+          cmd |= pack_thrust(r, l, rt_);
         }
       } else {
         const float *ap = (const float *)a.actions + row * A;
         n_cmd = A / 2;
 #pragma unroll
         for (int r = 0; r < R; r++)
-          if (r < n_cmd) {  // int(round(x)): round half to even (RR_Robot.py:100-102)
-            cl[r] = (int)rint((double)ap[2 * r]);
-            cr[r] = (int)rint((double)ap[2 * r + 1]);
-          }
+          if (r < n_cmd)  // int(round(x)): round half to even (RR_Robot.py:100-102)
+            cmd |= pack_thrust(r, (int)rint((double)ap[2 * r]), (int)rint((double)ap[2 * r + 1]));
       }
-      StepOut o;
-      sim_step(e, k, cl, cr, n_cmd, o);
+    }
+    StepOut o;
+    sim_step(e, k, cmd, n_cmd, o, live);
+    if (live) {
       e.ret_h += o.rew_h; e.ret_g += o.rew_g;
       last_naughty = rr_popc(o.naughty);
       st[RR_STAT_STEPS] += 1.0;
@@ -180,20 +210,19 @@ __global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ Consts 
       if (dim > 0 && (a.obs_h || a.obs_g)) {
         double ob[kMaxObs];
         unsigned oerr = 0;
-        if (a.obs_h) {
-          observe(e, k, 1, ob, oerr);
-          OutT *dst = (OutT *)a.obs_h + row * dim;
-          for (int q = 0; q < dim; q++) dst[q] = (OutT)ob[q];
-        }
-        if (a.obs_g) {
-          observe(e, k, -1, ob, oerr);
-          OutT *dst = (OutT *)a.obs_g + row * dim;
+#pragma unroll 1
+        for (int team = 1; team >= -1; team -= 2) {
+          OutT *dst = (OutT *)(team > 0 ? a.obs_h : a.obs_g);
+          if (!dst) continue;
+          observe(e, k, team, ob, oerr);
+          dst += row * dim;
+#pragma unroll 1
           for (int q = 0; q < dim; q++) dst[q] = (OutT)ob[q];
         }
       }
     }
-    store_env(e, a.sf, a.si, a.N, i, last_naughty);
   }
+  if (live) store_env<L>(e, a.sf, a.si, a.N, i, last_naughty);
   // episode statistics: warp-shuffle reduction, one atomic per warp and statistic
 #pragma unroll
   for (int q = 0; q < RR_NUM_STATS; q++) {
@@ -202,37 +231,43 @@ __global__ void __launch_bounds__(kBlock) k_step(const __grid_constant__ Consts 
   }
 }
 
-template <int NH, int NG, int NP, int NN>
-__global__ void __launch_bounds__(kBlock) k_init(const __grid_constant__ Consts k, double *sf, int32_t *si, int64_t N) {
-  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+template <class L>
+__global__ void __launch_bounds__(L::kMaxBlock, 1) k_init(const __grid_constant__ Consts k, double *sf, int32_t *si, int64_t N) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
-  Env<NH, NG, NP, NN> e;
+  typename L::E e;
+  double cold[L::E::kColdDoubles];
+  e.base = rr_smem + threadIdx.x;
+  e.cold = cold;
+  e.stride = (int)blockDim.x;
   construct_env(e);
   reset_env(e, k, (uint64_t)(k.env_offset + i));
-  store_env(e, sf, si, N, i, 0);
+  store_env<L>(e, sf, si, N, i, 0);
 }
 
-template <int NH, int NG, int NP, int NN>
-__global__ void __launch_bounds__(kBlock) k_reset(const __grid_constant__ Consts k, double *sf, int32_t *si, int64_t N,
-                                                  const uint8_t *mask) {
-  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+template <class L>
+__global__ void __launch_bounds__(L::kMaxBlock, 1) k_reset(const __grid_constant__ Consts k, double *sf, int32_t *si, int64_t N,
+                                                     const uint8_t *mask) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   if (mask && !mask[i]) return;
-  Env<NH, NG, NP, NN> e;
-  load_env(e, k, sf, si, N, i);
+  typename L::E e;
+  double cold[L::E::kColdDoubles];
+  load_env<L>(e, cold, k, sf, si, N, i);
   e.episode += 1;
   reset_env(e, k, (uint64_t)(k.env_offset + i));
-  store_env(e, sf, si, N, i, 0);
+  store_env<L>(e, sf, si, N, i, 0);
 }
 
-template <int NH, int NG, int NP, int NN, typename OutT>
-__global__ void __launch_bounds__(kBlock) k_observe(const __grid_constant__ Consts k, const double *sf, const int32_t *si,
-                                                    int64_t N, void *obs_h, void *obs_g) {
-  const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+template <class L, typename OutT>
+__global__ void __launch_bounds__(L::kMaxBlock, 1) k_observe(const __grid_constant__ Consts k, const double *sf, const int32_t *si,
+                                                       int64_t N, void *obs_h, void *obs_g) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
-  Env<NH, NG, NP, NN> e;
-  load_env(e, k, sf, si, N, i);
-  const int dim = obs_dim_of<NH, NG, NP, NN>(k.observer);
+  typename L::E e;
+  double cold[L::E::kColdDoubles];
+  load_env<L>(e, cold, k, sf, si, N, i);
+  const int dim = obs_dim_of<typename L::E>(k.observer);
   double ob[kMaxObs];
   unsigned oerr = 0;
   if (obs_h) {
@@ -257,6 +292,7 @@ struct rr_sim {
   Consts k;
   int64_t N;
   int device;
+  int sms = 148;
   int NH, NG, NP, NN, R, B, NF, NI;
   double *sf = nullptr;
   int32_t *si = nullptr;
@@ -306,17 +342,25 @@ int rr_default_config(rr_config *c, int preset, const char *env_id) {
   return RR_OK;
 }
 
-static inline unsigned grid_for(int64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+using LGame = Launch<2, 2, 4, 4>;
+using LTrain = Launch<1, 0, 1, 0>;
 
-#define DISPATCH_PRESET(s, CALL)                 \
-  do {                                           \
-    if ((s)->cfg.preset == RR_PRESET_GAME) {     \
-      constexpr int NH = 2, NG = 2, NP = 4, NN = 4; \
-      CALL;                                      \
-    } else {                                     \
-      constexpr int NH = 1, NG = 0, NP = 1, NN = 0; \
-      CALL;                                      \
-    }                                            \
+// Launch KERNEL<L, ...> for the handle's preset with the block size picked for its batch.
+#define LAUNCH_PRESET(s, st, KERNEL, ...)                                                                   \
+  do {                                                                                                      \
+    if ((s)->cfg.preset == RR_PRESET_GAME) {                                                                \
+      using L = LGame;                                                                                      \
+      auto kern = KERNEL;                                                                                   \
+      const int blk = pick_block((s)->N, (s)->sms, L::kMaxBlock);                                           \
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem_bytes(L::kMaxBlock)); \
+      kern<<<(unsigned)(((s)->N + blk - 1) / blk), blk, L::smem_bytes(blk), st>>>(__VA_ARGS__);             \
+    } else {                                                                                                \
+      using L = LTrain;                                                                                     \
+      auto kern = KERNEL;                                                                                   \
+      const int blk = pick_block((s)->N, (s)->sms, L::kMaxBlock);                                           \
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem_bytes(L::kMaxBlock)); \
+      kern<<<(unsigned)(((s)->N + blk - 1) / blk), blk, L::smem_bytes(blk), st>>>(__VA_ARGS__);             \
+    }                                                                                                       \
   } while (0)
 
 int rr_create(const rr_config *cfg, int64_t n_envs, int device, rr_sim **out) {
@@ -336,6 +380,8 @@ int rr_create(const rr_config *cfg, int64_t n_envs, int device, rr_sim **out) {
   s->k = make_consts(*cfg);
   s->N = n_envs;
   s->device = device;
+  cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, device);
+  if (s->sms <= 0) s->sms = 148;
   const bool game = cfg->preset == RR_PRESET_GAME;
   s->NH = game ? 2 : 1; s->NG = game ? 2 : 0; s->NP = game ? 4 : 1; s->NN = game ? 4 : 0;
   s->R = s->NH + s->NG; s->B = s->NP + s->NN;
@@ -350,7 +396,7 @@ int rr_create(const rr_config *cfg, int64_t n_envs, int device, rr_sim **out) {
   }
   s->stats = s->own_stats;
   CK(cudaMemset(s->stats, 0, sizeof(double) * RR_NUM_STATS));
-  DISPATCH_PRESET(s, (k_init<NH, NG, NP, NN><<<grid_for(n_envs), kBlock>>>(s->k, s->sf, s->si, s->N)));
+  LAUNCH_PRESET(s, (cudaStream_t)0, (k_init<L>), s->k, s->sf, s->si, s->N);
   s->launches++;
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
@@ -387,7 +433,7 @@ int rr_reset(rr_sim *s, const uint8_t *mask_dev, void *stream) {
   if (!s) return fail(RR_E_INVALID, "null handle");
   CK(cudaSetDevice(s->device));
   cudaStream_t st = (cudaStream_t)stream;
-  DISPATCH_PRESET(s, (k_reset<NH, NG, NP, NN><<<grid_for(s->N), kBlock, 0, st>>>(s->k, s->sf, s->si, s->N, mask_dev)));
+  LAUNCH_PRESET(s, st, (k_reset<L>), s->k, s->sf, s->si, s->N, mask_dev);
   s->launches++;
   CK(cudaGetLastError());
   return RR_OK;
@@ -399,9 +445,9 @@ int rr_observe(rr_sim *s, void *obs_h, void *obs_g, void *stream) {
   CK(cudaSetDevice(s->device));
   cudaStream_t st = (cudaStream_t)stream;
   if (s->cfg.out_f64)
-    DISPATCH_PRESET(s, (k_observe<NH, NG, NP, NN, double><<<grid_for(s->N), kBlock, 0, st>>>(s->k, s->sf, s->si, s->N, obs_h, obs_g)));
+    LAUNCH_PRESET(s, st, (k_observe<L, double>), s->k, s->sf, s->si, s->N, obs_h, obs_g);
   else
-    DISPATCH_PRESET(s, (k_observe<NH, NG, NP, NN, float><<<grid_for(s->N), kBlock, 0, st>>>(s->k, s->sf, s->si, s->N, obs_h, obs_g)));
+    LAUNCH_PRESET(s, st, (k_observe<L, float>), s->k, s->sf, s->si, s->N, obs_h, obs_g);
   s->launches++;
   CK(cudaGetLastError());
   return RR_OK;
@@ -430,9 +476,9 @@ int rr_step(rr_sim *s, const void *actions, int32_t n_actions, int32_t k_steps, 
   k.n_actions = n_actions;
   StepArgs a{s->sf, s->si, s->stats, actions, obs_h, obs_g, rew, done, s->N, k_steps};
   if (s->cfg.out_f64)
-    DISPATCH_PRESET(s, (k_step<NH, NG, NP, NN, double><<<grid_for(s->N), kBlock, 0, st>>>(k, a)));
+    LAUNCH_PRESET(s, st, (k_step<L, double>), k, a);
   else
-    DISPATCH_PRESET(s, (k_step<NH, NG, NP, NN, float><<<grid_for(s->N), kBlock, 0, st>>>(k, a)));
+    LAUNCH_PRESET(s, st, (k_step<L, float>), k, a);
   s->launches++;
   CK(cudaGetLastError());
   return RR_OK;

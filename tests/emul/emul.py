@@ -40,6 +40,8 @@ def lib():
         L.emul_reset.restype = C.c_uint
         L.emul_observe.argtypes = [C.POINTER(Config), vp, vp, vp, vp, vp, C.c_int, vp]
         L.emul_observe.restype = C.c_uint
+        L.emul_predicates.argtypes = [C.POINTER(Config), vp, vp, vp, vp, vp, vp, vp]
+        L.emul_predicates.restype = None
         _lib = L
     return _lib
 
@@ -83,3 +85,13 @@ class EmulEnv:
         lib().emul_observe(C.byref(self.cfg), _p(self.rob), _p(self.rhist), _p(self.rflag), _p(self.ball),
                            _p(self.stepc), int(team), _p(o))
         return o[:self.obs_dim]
+
+
+def predicates(cfg, st):
+    """(rr[6], br[32]) int arrays: bit0 = cheap rejection fired, bit1 = reference predicate True."""
+    rob = np.ascontiguousarray(st["rob"], np.float64); rhist = np.ascontiguousarray(st["rhist"], np.float64)
+    rflag = np.ascontiguousarray(st["rflag"], np.int32); ball = np.ascontiguousarray(st["ball"], np.float64)
+    step = np.zeros(1, np.int32)
+    rr = np.zeros(6, np.int32); br = np.zeros(32, np.int32)
+    lib().emul_predicates(C.byref(cfg), _p(rob), _p(rhist), _p(rflag), _p(ball), _p(step), _p(rr), _p(br))
+    return rr, br

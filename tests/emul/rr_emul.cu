@@ -11,40 +11,50 @@
 using namespace rr;
 
 template <int NH, int NG, int NP, int NN>
-static void load(Env<NH, NG, NP, NN> &e, const Consts &k, const double *rob, const double *rhist, const int32_t *rflag,
-                 const double *ball, int32_t step) {
+struct HostEnv {
   using E = Env<NH, NG, NP, NN>;
+  double buf[E::kDoubles];
+  double cold[E::kColdDoubles];
+  E e;
+  HostEnv() { std::memset(buf, 0, sizeof buf); std::memset(cold, 0, sizeof cold); e.base = buf; e.cold = cold; e.stride = 1; e.thrust = 0x88888888u; e.hvalid = 0; e.step = 0; e.err = 0; e.episode = 0; e.ret_h = e.ret_g = 0; }
+};
+
+template <class E>
+static void load(E &e, const Consts &k, const double *rob, const double *rhist, const int32_t *rflag,
+                 const double *ball, int32_t step) {
   e.hvalid = 0;
+  e.thrust = 0x88888888u;
+  e.masks_dirty = true;
+  e.br_near = e.bb_near = e.rr_near = e.wall_near = e.moving = 0;
   for (int r = 0; r < E::R; r++) {
     const double *p = rob + 7 * r;
-    e.rcx[r] = p[0]; e.rcy[r] = p[1]; e.rl[r] = p[2]; e.rr[r] = p[3]; e.rt[r] = p[4]; e.rb[r] = p[5]; e.rrot[r] = p[6];
-    e.hx[r] = rhist[3 * r]; e.hy[r] = rhist[3 * r + 1]; e.hrot[r] = rhist[3 * r + 2];
-    e.thl[r] = rflag[3 * r]; e.thr[r] = rflag[3 * r + 1];
+    e.rcx(r) = p[0]; e.rcy(r) = p[1]; e.rl(r) = p[2]; e.rr(r) = p[3]; e.rt(r) = p[4]; e.rb(r) = p[5]; e.rrot(r) = p[6];
+    e.hx(r) = rhist[3 * r]; e.hy(r) = rhist[3 * r + 1]; e.hrot(r) = rhist[3 * r + 2];
+    e.set_thrust(r, rflag[3 * r], rflag[3 * r + 1]);
     if (rflag[3 * r + 2]) e.hvalid |= 1u << r;
     robot_refresh_corners(e, k, r);
   }
   for (int b = 0; b < E::B; b++) {
     const double *p = ball + 8 * b;
-    e.bcx[b] = p[0]; e.bcy[b] = p[1]; e.bl[b] = p[2]; e.br[b] = p[3]; e.bt[b] = p[4]; e.bb[b] = p[5];
-    e.bvx[b] = p[6]; e.bvy[b] = p[7];
+    e.bcx(b) = p[0]; e.bcy(b) = p[1]; e.bl(b) = p[2]; e.br(b) = p[3]; e.bt(b) = p[4]; e.bb(b) = p[5];
+    e.bvx(b) = p[6]; e.bvy(b) = p[7];
   }
   e.step = step; e.err = 0; e.episode = 0; e.ret_h = e.ret_g = 0;
 }
 
-template <int NH, int NG, int NP, int NN>
-static void store(const Env<NH, NG, NP, NN> &e, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step) {
-  using E = Env<NH, NG, NP, NN>;
+template <class E>
+static void store(const E &e, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step) {
   for (int r = 0; r < E::R; r++) {
     double *p = rob + 7 * r;
-    p[0] = e.rcx[r]; p[1] = e.rcy[r]; p[2] = e.rl[r]; p[3] = e.rr[r]; p[4] = e.rt[r]; p[5] = e.rb[r]; p[6] = e.rrot[r];
+    p[0] = e.rcx(r); p[1] = e.rcy(r); p[2] = e.rl(r); p[3] = e.rr(r); p[4] = e.rt(r); p[5] = e.rb(r); p[6] = e.rrot(r);
     int v = (e.hvalid >> r) & 1;
-    rhist[3 * r] = v ? e.hx[r] : 0; rhist[3 * r + 1] = v ? e.hy[r] : 0; rhist[3 * r + 2] = v ? e.hrot[r] : 0;
-    rflag[3 * r] = e.thl[r]; rflag[3 * r + 1] = e.thr[r]; rflag[3 * r + 2] = v;
+    rhist[3 * r] = v ? e.hx(r) : 0; rhist[3 * r + 1] = v ? e.hy(r) : 0; rhist[3 * r + 2] = v ? e.hrot(r) : 0;
+    rflag[3 * r] = e.thl(r); rflag[3 * r + 1] = e.thr(r); rflag[3 * r + 2] = v;
   }
   for (int b = 0; b < E::B; b++) {
     double *p = ball + 8 * b;
-    p[0] = e.bcx[b]; p[1] = e.bcy[b]; p[2] = e.bl[b]; p[3] = e.br[b]; p[4] = e.bt[b]; p[5] = e.bb[b];
-    p[6] = e.bvx[b]; p[7] = e.bvy[b];
+    p[0] = e.bcx(b); p[1] = e.bcy(b); p[2] = e.bl(b); p[3] = e.br(b); p[4] = e.bt(b); p[5] = e.bb(b);
+    p[6] = e.bvx(b); p[7] = e.bvy(b);
   }
   *step = e.step;
 }
@@ -53,22 +63,26 @@ template <int NH, int NG, int NP, int NN>
 static unsigned step_t(const Consts &k, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,
                        const double *actions, int n_actions, double *obs_h, double *obs_g, double *rew, int32_t *done,
                        int32_t *naughty) {
-  using E = Env<NH, NG, NP, NN>;
-  E e;
+  HostEnv<NH, NG, NP, NN> h;
+  auto &e = h.e;
+  using E = typename HostEnv<NH, NG, NP, NN>::E;
   load(e, k, rob, rhist, rflag, ball, *step);
-  int cl[E::R], cr[E::R], n_cmd;
+  unsigned cmd = 0;
+  int n_cmd;
   if (k.discrete) {
     n_cmd = n_actions;
-    for (int r = 0; r < n_cmd && r < E::R; r++) thrust_from_direction((int)actions[r], cl[r], cr[r]);
+    for (int r = 0; r < n_cmd && r < E::R; r++) {
+      int l, rt;
+      thrust_from_direction((int)actions[r], l, rt);
+      cmd |= pack_thrust(r, l, rt);
+    }
   } else {
     n_cmd = n_actions / 2;
-    for (int r = 0; r < n_cmd && r < E::R; r++) {
-      cl[r] = (int)rint((double)(float)actions[2 * r]);
-      cr[r] = (int)rint((double)(float)actions[2 * r + 1]);
-    }
+    for (int r = 0; r < n_cmd && r < E::R; r++)
+      cmd |= pack_thrust(r, (int)rint((double)(float)actions[2 * r]), (int)rint((double)(float)actions[2 * r + 1]));
   }
   StepOut o;
-  sim_step(e, k, cl, cr, n_cmd, o);
+  sim_step(e, k, cmd, n_cmd, o, true);
   unsigned oerr = 0;
   if (obs_h) observe(e, k, 1, obs_h, oerr);
   if (obs_g) observe(e, k, -1, obs_g, oerr);
@@ -82,7 +96,8 @@ static unsigned step_t(const Consts &k, double *rob, double *rhist, int32_t *rfl
 template <int NH, int NG, int NP, int NN>
 static unsigned reset_t(const Consts &k, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,
                         uint64_t env, uint32_t episode, int construct) {
-  Env<NH, NG, NP, NN> e;
+  HostEnv<NH, NG, NP, NN> h;
+  auto &e = h.e;
   if (construct) construct_env(e);
   else load(e, k, rob, rhist, rflag, ball, *step);
   e.episode = episode;
@@ -116,10 +131,29 @@ unsigned emul_observe(const rr_config *cfg, double *rob, double *rhist, int32_t 
   Consts k = make_consts(*cfg);
   unsigned err = 0;
   if (cfg->preset == RR_PRESET_GAME) {
-    Env<2, 2, 4, 4> e; load(e, k, rob, rhist, rflag, ball, *step); observe(e, k, team, obs, err);
+    HostEnv<2, 2, 4, 4> h; load(h.e, k, rob, rhist, rflag, ball, *step); observe(h.e, k, team, obs, err);
   } else {
-    Env<1, 0, 1, 0> e; load(e, k, rob, rhist, rflag, ball, *step); observe(e, k, team, obs, err);
+    HostEnv<1, 0, 1, 0> h; load(h.e, k, rob, rhist, rflag, ball, *step); observe(h.e, k, team, obs, err);
   }
   return err;
 }
+
+// For every (robot, robot) and (ball, robot) pair of a GAME state: bit0 = the cheap rejection fired,
+// bit1 = the reference predicate is True.  A pair with both bits set would be a parity bug.
+void emul_predicates(const rr_config *cfg, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,
+                     int32_t *rr_out /*[6]*/, int32_t *br_out /*[32]*/) {
+  Consts k = make_consts(*cfg);
+  HostEnv<2, 2, 4, 4> h;
+  auto &e = h.e;
+  load(e, k, rob, rhist, rflag, ball, *step);
+  unsigned err = 0;
+  int n = 0;
+  for (int i = 0; i < 4; i++)
+    for (int j = i + 1; j < 4; j++, n++)
+      rr_out[n] = (robots_separated(e, i, j) ? 1 : 0) | (robots_collided(e, i, j, err) ? 2 : 0);
+  for (int b = 0; b < 8; b++)
+    for (int r = 0; r < 4; r++)
+      br_out[b * 4 + r] = (ball_clear_of_robot(e, b, r) ? 1 : 0) | (ball_robot_collided(e, k, b, r, err) ? 2 : 0);
 }
+}
+

@@ -119,3 +119,52 @@ def test_philox_known_answer(oracle):
     assert oracle.philox4x32([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     assert oracle.philox4x32([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def test_fast_rejections_never_contradict_reference_predicates():
+    """robots_separated / ball_clear_of_robot (the cheap culls in front of robots_collided and
+    ball_robot_collided) must only fire when the reference predicate is False.  Random GAME states
+    concentrated around first contact, incl. axis-aligned and equal headings."""
+    from emul.emul import predicates
+    from roborugby_b200 import _lib
+    cfg = _lib.default_config(_lib.PRESET_GAME, "RoboRugbySimpleDuel-v2")
+    rng = np.random.default_rng(7)
+    n_fire = n_true = n_both = 0
+    for it in range(6000):
+        rot = rng.uniform(0, 360, 4)
+        if it % 3 == 0:
+            rot = rng.choice([0, 45, 90, 135, 180, 270, 33.3, 33.3 + 90], 4).astype(float)
+        rot = (rot + 720) % 360
+        c = rng.uniform(150, 650, (4, 2))
+        for j in range(1, 4):  # robots j placed around robot 0 at touching-ish distances
+            ang = rng.uniform(0, 2 * np.pi)
+            d = rng.uniform(18, 48)
+            c[j] = c[0] + d * np.array([np.cos(ang), np.sin(ang)])
+        rob = np.zeros((4, 7))
+        rob[:, 0:2] = c
+        rob[:, 6] = rot
+        rob[:, 2] = c[:, 0] - 25; rob[:, 3] = c[:, 0] + 25; rob[:, 4] = c[:, 1] - 25; rob[:, 5] = c[:, 1] + 25
+        ball = np.zeros((8, 8))
+        for b in range(8):  # balls hugging robot b % 4 at the contact distance +- a little
+            r = b % 4
+            th = np.radians(rot[r])
+            ux, uy = np.cos(th), -np.sin(th)      # heading (length axis), y down
+            vx, vy = np.sin(th), np.cos(th)       # width axis
+            lu = rng.uniform(-19, 19); lv = rng.uniform(-29, 29)
+            if b < 4:  # put it right at the surface
+                side = rng.integers(3)
+                gap = rng.choice([7.0, 7.005, 7.02, 6.99, 7.0 + rng.uniform(-0.05, 0.05)])
+                if side == 0: lu = np.sign(lu) * (10 + gap)
+                elif side == 1: lv = np.sign(lv) * (20 + gap)
+                else:
+                    a2 = rng.uniform(0, np.pi / 2)
+                    lu = np.sign(lu) * (10 + gap * np.cos(a2)); lv = np.sign(lv) * (20 + gap * np.sin(a2))
+            p = c[r] + lu * np.array([ux, uy]) + lv * np.array([vx, vy])
+            ball[b, 0:2] = p
+            ball[b, 2] = p[0] - 7; ball[b, 3] = p[0] + 7; ball[b, 4] = p[1] - 7; ball[b, 5] = p[1] + 7
+        st = dict(rob=rob, rhist=np.zeros((4, 3)), rflag=np.zeros((4, 3), np.int32), ball=ball, step=0)
+        rr, br = predicates(cfg, st)
+        for v in list(rr) + list(br):
+            n_fire += v & 1; n_true += (v >> 1) & 1; n_both += (v == 3)
+    assert n_both == 0, f"{n_both} pairs rejected although the reference predicate is True"
+    assert n_fire > 10000 and n_true > 10000, (n_fire, n_true)  # the sample really straddles the boundary
