@@ -40,6 +40,10 @@ def lib():
         L.emul_reset.restype = C.c_uint
         L.emul_observe.argtypes = [C.POINTER(Config), vp, vp, vp, vp, vp, C.c_int, vp]
         L.emul_observe.restype = C.c_uint
+        L.emul_use_libm_sincos.argtypes = [C.c_int]
+        L.emul_use_libm_sincos.restype = None
+        L.emul_sincos.argtypes = [vp, C.c_int, vp, vp]
+        L.emul_sincos.restype = None
         L.emul_predicates.argtypes = [C.POINTER(Config), vp, vp, vp, vp, vp, vp, vp]
         L.emul_predicates.restype = None
         _lib = L
@@ -95,3 +99,16 @@ def predicates(cfg, st):
     rr = np.zeros(6, np.int32); br = np.zeros(32, np.int32)
     lib().emul_predicates(C.byref(cfg), _p(rob), _p(rhist), _p(rflag), _p(ball), _p(step), _p(rr), _p(br))
     return rr, br
+
+
+def sincos(x):
+    x = np.ascontiguousarray(x, np.float64)
+    s = np.empty_like(x); c = np.empty_like(x)
+    lib().emul_sincos(_p(x), x.size, _p(s), _p(c))
+    return s, c
+
+
+def use_libm_sincos(on):
+    """True: the host build calls glibc sin/cos (bit-identical trig to the oracle, isolates the kernel
+    LOGIC); False (default): rr_sincos_dd, the routine the GPU executes."""
+    lib().emul_use_libm_sincos(int(bool(on)))

@@ -155,5 +155,13 @@ void emul_predicates(const rr_config *cfg, double *rob, double *rhist, int32_t *
     for (int r = 0; r < 4; r++)
       br_out[b * 4 + r] = (ball_clear_of_robot(e, b, r) ? 1 : 0) | (ball_robot_collided(e, k, b, r, err) ? 2 : 0);
 }
+
+// n evaluations of the simulator's sin/cos routine (rr_sincos.cuh) on the host.
+void emul_sincos(const double *x, int n, double *s, double *c) {
+  for (int i = 0; i < n; i++) rr_sincos_dd(x[i], &s[i], &c[i]);
+}
+
+// 1: glibc sin/cos (what the oracle uses), 0: rr_sincos_dd (what the GPU uses)
+void emul_use_libm_sincos(int on) { rr::g_host_libm_sincos = on; }
 }
 

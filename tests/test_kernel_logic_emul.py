@@ -15,6 +15,16 @@ from parity_util import compare_record
 FILES = [f for f in golden_files("*.npz") if parse_name(f)[2] in ("random", "chase", "sticky", "inject")]
 
 
+@pytest.fixture(params=["libm", "dd"])
+def trig(request):
+    """libm: glibc sin/cos in the host build -> isolates the kernel logic (must agree with the oracle to the
+    last bit wherever the scratch rect is not involved); dd: the table-driven routine the GPU runs."""
+    from emul import emul
+    emul.use_libm_sincos(request.param == "libm")
+    yield request.param
+    emul.use_libm_sincos(False)
+
+
 def _make(path):
     from emul.emul import EmulEnv
     from roborugby_b200 import _lib
@@ -29,7 +39,7 @@ def _make(path):
 
 
 @pytest.mark.parametrize("path", FILES, ids=[p.split("/")[-1] for p in FILES])
-def test_kernel_source_matches_reference_golden(path):
+def test_kernel_source_matches_reference_golden(path, trig):
     d, cfg, env, preset, env_id = _make(path)
     n, T = d["act"].shape[:2]
     bad, exact, worst, total = [], 0, 0.0, 0
@@ -60,11 +70,17 @@ def test_kernel_source_matches_reference_golden(path):
 
 
 @pytest.mark.parametrize("path", FILES[:6], ids=[p.split("/")[-1] for p in FILES[:6]])
-def test_kernel_source_matches_oracle_trajectories(oracle, path):
-    """Multi-step: both sides run the whole trajectory from the first state only."""
+def test_kernel_source_matches_oracle_trajectories(oracle, path, trig):
+    """Multi-step: both sides run the whole trajectory from the first state only.
+
+    With glibc trig every step must agree.  With the GPU's own sin/cos a last-bit difference (glibc is not
+    correctly rounded in ~0.13 % of calls, tests/test_sincos.py) may flip a contact decision; after the
+    first flip the two chaotic trajectories are no longer comparable, so the trajectory is dropped from
+    there and the number of such trajectories is bounded."""
     d, cfg, env, preset, env_id = _make(path)
     n, T = d["act"].shape[:2]
     oracle.scratch_mode(1)
+    diverged = 0
     try:
         o = oracle.OracleEnv(preset, env_id)
         for i in range(n):
@@ -78,7 +94,11 @@ def test_kernel_source_matches_oracle_trajectories(oracle, path):
                 if want["err"]:
                     continue
                 ok, _, w, why = compare_record(env.get_state(), got, o.get_state(), want)
+                if not ok and trig == "dd":
+                    diverged += 1
+                    break
                 assert ok, (i, t, why, w)
+        assert diverged <= max(1, n // 3), f"{diverged} of {n} trajectories diverged"
     finally:
         oracle.scratch_mode(0)
 
