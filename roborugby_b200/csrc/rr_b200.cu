@@ -36,7 +36,10 @@ struct Launch {
   using E = Env<NH, NG, NP, NN>;
   // largest block: bounded by 227 KB of shared memory and by 65 536 registers per SM
   static constexpr int kMaxBlock = R > 1 ? 448 : 512;
-  static constexpr size_t smem_bytes(int block) { return sizeof(double) * E::kDoubles * (size_t)block; }
+  static constexpr int kTrigDoubles = kSinCosRows * 4;  // sin/cos table staged in front of the env fields
+  static constexpr size_t smem_bytes(int block) {
+    return sizeof(double) * (kTrigDoubles + E::kDoubles * (size_t)block);
+  }
   // HBM structure-of-arrays layout
   static constexpr int kRobotF = 10, kBallF = 8;
   static constexpr int NF = R * kRobotF + B * kBallF + 2;
@@ -54,11 +57,20 @@ static inline int pick_block(int64_t n, int sms, int max_block) {
 
 extern __shared__ double rr_smem[];
 
+// Stage the sin/cos table in shared memory (all threads of the block; followed by a barrier).
+__device__ __forceinline__ const double *stage_trig_table() {
+  const double *src = &kSinCosDev[0][0];
+  for (int q = threadIdx.x; q < kSinCosRows * 4; q += blockDim.x) rr_smem[q] = src[q];
+  __syncthreads();
+  return rr_smem;
+}
+__device__ __forceinline__ double *env_smem_base() { return rr_smem + kSinCosRows * 4 + threadIdx.x; }
+
 // HBM column -> (hot shared / cold local) fields.  Robot columns: cx,cy,l,r,t,b,rot,hx,hy,hrot.
 template <class L>
 __device__ __forceinline__ void load_env(typename L::E &e, double *cold, const Consts &k, const double *__restrict__ sf,
                                          const int32_t *__restrict__ si, int64_t N, int64_t i) {
-  e.base = rr_smem + threadIdx.x;
+  e.base = env_smem_base();
   e.cold = cold;
   e.stride = (int)blockDim.x;
   int f = 0;
@@ -146,10 +158,11 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_step(const __grid_constant_
   for (int q = 0; q < RR_NUM_STATS; q++) st[q] = 0.0;
   E e;
   double cold[E::kColdDoubles];
+  e.trig = stage_trig_table();
   if (live) {
     load_env<L>(e, cold, k, a.sf, a.si, a.N, i);
   } else {
-    e.base = rr_smem + threadIdx.x; e.cold = cold; e.stride = (int)blockDim.x;
+    e.base = env_smem_base(); e.cold = cold; e.stride = (int)blockDim.x;
     e.err = 0; e.step = 0; e.masks_dirty = false;
   }
   const int dim = obs_dim_of<E>(k.observer);
@@ -237,7 +250,8 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_init(const __grid_constant_
   if (i >= N) return;
   typename L::E e;
   double cold[L::E::kColdDoubles];
-  e.base = rr_smem + threadIdx.x;
+  e.trig = &kSinCosDev[0][0];
+  e.base = env_smem_base();
   e.cold = cold;
   e.stride = (int)blockDim.x;
   construct_env(e);
@@ -253,6 +267,7 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_reset(const __grid_constant
   if (mask && !mask[i]) return;
   typename L::E e;
   double cold[L::E::kColdDoubles];
+  e.trig = &kSinCosDev[0][0];
   load_env<L>(e, cold, k, sf, si, N, i);
   e.episode += 1;
   reset_env(e, k, (uint64_t)(k.env_offset + i));
@@ -266,6 +281,7 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_observe(const __grid_consta
   if (i >= N) return;
   typename L::E e;
   double cold[L::E::kColdDoubles];
+  e.trig = &kSinCosDev[0][0];
   load_env<L>(e, cold, k, sf, si, N, i);
   const int dim = obs_dim_of<typename L::E>(k.observer);
   double ob[kMaxObs];

@@ -133,7 +133,10 @@ __device__ const double kSinCosDev[kSinCosRows][4] = {RR_SINCOS_ROWS};
 RR_HD __forceinline__ double rr_fma(double a, double b, double c) { return fma(a, b, c); }
 
 // Valid for |x| < 16 (n <= 10 keeps n*p1 and n*p2 exact); the simulator's arguments lie in [-1.6, 7.9].
-RR_HD __noinline__ void rr_sincos_dd(double x, double *sp, double *cp) {
+// `tab` = the table to read: kSinCosHost on the host, on the GPU a copy of kSinCosDev that the kernel
+// staged in shared memory (the four dependent-address loads then cost a shared-memory access instead of
+// an L1/L2 round trip in the hottest routine of the kernel).
+RR_HD __noinline__ void rr_sincos_dd(double x, double *sp, double *cp, const double *tab) {
   if (!(fabs(x) < 16.0)) {  // not produced by the simulator; keep libm semantics for inf/nan/huge
     sincos(x, sp, cp);
     return;
@@ -172,11 +175,7 @@ RR_HD __noinline__ void rr_sincos_dd(double x, double *sp, double *cp) {
   double tt = th + rl;
   double tl = rl - (tt - th);                  // Fast2Sum(th, rl): |th| >= |rl| unless th == 0 (then exact)
   th = tt;
-#ifdef __CUDA_ARCH__
-  const double Sh = kSinCosDev[i][0], Sl = kSinCosDev[i][1], Ch = kSinCosDev[i][2], Cl = kSinCosDev[i][3];
-#else
-  const double Sh = kSinCosHost[i][0], Sl = kSinCosHost[i][1], Ch = kSinCosHost[i][2], Cl = kSinCosHost[i][3];
-#endif
+  const double Sh = tab[4 * i], Sl = tab[4 * i + 1], Ch = tab[4 * i + 2], Cl = tab[4 * i + 3];
   const double t2 = th * th;
   // sin t - t = t^3 * (-1/6 + t^2/120 - t^4/5040) ; 1 - cos t = t^2 * (1/2 - t^2/24 + t^4/720)
   const double ps = th * t2 * (-0x1.5555555555555p-3 + t2 * (0x1.1111111111111p-7 - t2 * 0x1.a01a01a01a01ap-13));

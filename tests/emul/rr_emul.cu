@@ -16,7 +16,7 @@ struct HostEnv {
   double buf[E::kDoubles];
   double cold[E::kColdDoubles];
   E e;
-  HostEnv() { std::memset(buf, 0, sizeof buf); std::memset(cold, 0, sizeof cold); e.base = buf; e.cold = cold; e.stride = 1; e.thrust = 0x88888888u; e.hvalid = 0; e.step = 0; e.err = 0; e.episode = 0; e.ret_h = e.ret_g = 0; }
+  HostEnv() { std::memset(buf, 0, sizeof buf); std::memset(cold, 0, sizeof cold); e.base = buf; e.cold = cold; e.stride = 1; e.trig = &kSinCosHost[0][0]; e.thrust = 0x88888888u; e.hvalid = 0; e.step = 0; e.err = 0; e.episode = 0; e.ret_h = e.ret_g = 0; }
 };
 
 template <class E>
@@ -158,7 +158,7 @@ void emul_predicates(const rr_config *cfg, double *rob, double *rhist, int32_t *
 
 // n evaluations of the simulator's sin/cos routine (rr_sincos.cuh) on the host.
 void emul_sincos(const double *x, int n, double *s, double *c) {
-  for (int i = 0; i < n; i++) rr_sincos_dd(x[i], &s[i], &c[i]);
+  for (int i = 0; i < n; i++) rr_sincos_dd(x[i], &s[i], &c[i], &kSinCosHost[0][0]);
 }
 
 // 1: glibc sin/cos (what the oracle uses), 0: rr_sincos_dd (what the GPU uses)
