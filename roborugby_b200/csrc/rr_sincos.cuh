@@ -132,14 +132,18 @@ __device__ const double kSinCosDev[kSinCosRows][4] = {RR_SINCOS_ROWS};
 
 RR_HD __forceinline__ double rr_fma(double a, double b, double c) { return fma(a, b, c); }
 
-// Valid for |x| < 16 (n <= 10 keeps n*p1 and n*p2 exact); the simulator's arguments lie in [-1.6, 7.9].
+struct SinCos { double s, c; };  // returned in registers (no pointer outputs: those force local-memory traffic)
+
 // `tab` = the table to read: kSinCosHost on the host, on the GPU a copy of kSinCosDev that the kernel
 // staged in shared memory (the four dependent-address loads then cost a shared-memory access instead of
 // an L1/L2 round trip in the hottest routine of the kernel).
-RR_HD __noinline__ void rr_sincos_dd(double x, double *sp, double *cp, const double *tab) {
+// Valid for |x| < 16 (n <= 10 keeps n*p1 and n*p2 exact); the simulator's arguments lie in [-1.6, 7.9].
+// Every multiply-add below is an explicit fma, so the host build and the GPU round identically.
+RR_HD __noinline__ SinCos rr_sincos_dd(double x, const double *tab) {
+  SinCos out;
   if (!(fabs(x) < 16.0)) {  // not produced by the simulator; keep libm semantics for inf/nan/huge
-    sincos(x, sp, cp);
-    return;
+    sincos(x, &out.s, &out.c);
+    return out;
   }
   const double kTwoOverPi = 0x1.45f306dc9c883p-1;
   const double p1 = 0x1.921fb544p+0;          // 33 bits of pi/2
@@ -148,65 +152,59 @@ RR_HD __noinline__ void rr_sincos_dd(double x, double *sp, double *cp, const dou
   const double p4 = 0x1.129024e088a68p-123;
   const double n = rint(x * kTwoOverPi);
   // r = x - n*pi/2 as rh + rl
-  double t1 = x - n * p1;                      // exact
-  double q = n * p2;                           // exact (n < 2^4, p2 has 33 bits)
+  const double t1 = rr_fma(-n, p1, x);         // exact (n*p1 has <= 37 bits, the difference is representable)
+  const double q = n * p2;                     // exact (n < 2^4, p2 has 33 bits)
   double rh = t1 - q;
-  double rl;
-  {
-    const double bv = rh - t1;                 // TwoSum(t1, -q)
-    rl = (t1 - (rh - bv)) + (-q - bv);
-  }
-  double q3 = n * p3;
-  double q3e = rr_fma(n, p3, -q3);
-  // (rh, rl) -= q3 + q3e + n*p4
-  double s1 = rh - q3;
-  double bb = s1 - rh;
-  double e1 = (rh - (s1 - bb)) + (-q3 - bb);   // TwoSum(rh, -q3)
-  rl = rl + e1 - q3e - n * p4;
+  const double bv = rh - t1;                   // TwoSum(t1, -q)
+  double rl = (t1 - (rh - bv)) + (-q - bv);
+  const double q3 = n * p3;
+  const double q3e = rr_fma(n, p3, -q3);
+  const double s1 = rh - q3;
+  const double bb = s1 - rh;
+  const double e1 = (rh - (s1 - bb)) + (-q3 - bb);   // TwoSum(rh, -q3)
+  rl = (rl + e1) - rr_fma(n, p4, q3e);
   rh = s1 + rl;
   rl = rl - (rh - s1);                         // renormalise
   // |r| = xi + t
   const bool neg = rh < 0.0;
-  if (neg) { rh = -rh; rl = -rl; }
+  rh = fabs(rh);
+  rl = neg ? -rl : rl;
   const double fi = rint(rh * 128.0);
   const int i = (int)fi;
-  const double xi = fi * 0.0078125;
-  double th = rh - xi;                          // exact
-  double tt = th + rl;
-  double tl = rl - (tt - th);                  // Fast2Sum(th, rl): |th| >= |rl| unless th == 0 (then exact)
+  double th = rr_fma(fi, -0.0078125, rh);      // rh - i/128, exact
+  const double tt = th + rl;
+  const double tl = rl - (tt - th);            // Fast2Sum(th, rl): |th| >= |rl| unless th == 0 (then exact)
   th = tt;
   const double Sh = tab[4 * i], Sl = tab[4 * i + 1], Ch = tab[4 * i + 2], Cl = tab[4 * i + 3];
   const double t2 = th * th;
   // sin t - t = t^3 * (-1/6 + t^2/120 - t^4/5040) ; 1 - cos t = t^2 * (1/2 - t^2/24 + t^4/720)
-  const double ps = th * t2 * (-0x1.5555555555555p-3 + t2 * (0x1.1111111111111p-7 - t2 * 0x1.a01a01a01a01ap-13));
-  const double pc = t2 * (0.5 - t2 * (0x1.5555555555555p-5 - t2 * 0x1.6c16c16c16c17p-10));
+  const double ps = (th * t2) * rr_fma(t2, rr_fma(t2, -0x1.a01a01a01a01ap-13, 0x1.1111111111111p-7), -0x1.5555555555555p-3);
+  const double pc = t2 * rr_fma(t2, rr_fma(t2, 0x1.6c16c16c16c17p-10, -0x1.5555555555555p-5), 0.5);
   // sin(xi + t) = Sh + Ch*th + [Sl + Ch*tl + Cl*th + Ch*ps - Sh*pc]
   double s, c;
   {
     const double p = Ch * th, pe = rr_fma(Ch, th, -p);
     const double a = Sh + p;
     const double b = (Sh - a) + p;              // Fast2Sum: |Sh| >= |p| except i == 0 where Sh == 0 (exact)
-    const double rest = ((Ch * ps - Sh * pc) + (Ch * tl + Cl * th)) + Sl;
+    const double rest = rr_fma(Ch, ps, rr_fma(-Sh, pc, rr_fma(Ch, tl, rr_fma(Cl, th, Sl))));
     s = a + ((b + pe) + rest);
   }
-  // cos(xi + t) = Ch - Sh*th - [ -Cl + Sh*tl + Sl*th + Sh*ps + Ch*pc ]
+  // cos(xi + t) = Ch - Sh*th + [Cl - Sh*tl - Sl*th - Sh*ps - Ch*pc]
   {
     const double p = Sh * th, pe = rr_fma(Sh, th, -p);
     const double a = Ch - p;
     const double b = (Ch - a) - p;
-    const double rest = Cl - ((Sh * ps + Ch * pc) + (Sh * tl + Sl * th));
+    const double rest = rr_fma(-Sh, ps, rr_fma(-Ch, pc, rr_fma(-Sh, tl, rr_fma(-Sl, th, Cl))));
     c = a + ((b - pe) + rest);
   }
-  if (neg) s = -s;
+  s = neg ? -s : s;
   const int quad = ((int)n) & 3;
-  double so, co;
-  switch (quad) {
-    case 0: so = s; co = c; break;
-    case 1: so = c; co = -s; break;
-    case 2: so = -s; co = -c; break;
-    default: so = -c; co = s; break;
-  }
-  *sp = so; *cp = co;
+  const bool swap = quad & 1;
+  const double so = swap ? c : s, co = swap ? s : c;
+  // quad 0: (s, c)  1: (c, -s)  2: (-s, -c)  3: (-c, s)
+  out.s = (quad & 2) ? -so : so;
+  out.c = (quad == 1 || quad == 2) ? -co : co;
+  return out;
 }
 
 }  // namespace rr

@@ -158,7 +158,7 @@ void emul_predicates(const rr_config *cfg, double *rob, double *rhist, int32_t *
 
 // n evaluations of the simulator's sin/cos routine (rr_sincos.cuh) on the host.
 void emul_sincos(const double *x, int n, double *s, double *c) {
-  for (int i = 0; i < n; i++) rr_sincos_dd(x[i], &s[i], &c[i], &kSinCosHost[0][0]);
+  for (int i = 0; i < n; i++) { SinCos r = rr_sincos_dd(x[i], &kSinCosHost[0][0]); s[i] = r.s; c[i] = r.c; }
 }
 
 // 1: glibc sin/cos (what the oracle uses), 0: rr_sincos_dd (what the GPU uses)
