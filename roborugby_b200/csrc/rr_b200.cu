@@ -84,6 +84,7 @@ __device__ __forceinline__ void load_env(typename L::E &e, double *cold, const C
     for (int q = 0; q < 7; q++) e.rf(r, q) = sf[(f + q) * N + i];
 #pragma unroll
     for (int q = 0; q < 3; q++) e.rc(r, q) = sf[(f + 7 + q) * N + i];
+    e.rc(r, 3) = rr_nan(); e.rc(r, 8) = rr_nan();  // heading-keyed caches start empty
     f += L::kRobotF;
     int32_t p = si[r * N + i];
     e.set_thrust(r, (int)(int8_t)(p & 0xff), (int)(int8_t)((p >> 8) & 0xff));
@@ -156,9 +157,15 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_step(const __grid_constant_
   double st[RR_NUM_STATS];
 #pragma unroll
   for (int q = 0; q < RR_NUM_STATS; q++) st[q] = 0.0;
+#ifdef RR_DEBUG_CLOCK
+  const long long dbg_t0 = clock64();
+#endif
   E e;
   double cold[E::kColdDoubles];
   e.trig = stage_trig_table();
+#ifdef RR_DEBUG_COUNT
+  e.dbg[0] = e.dbg[1] = e.dbg[2] = e.dbg[3] = 0;
+#endif
   if (live) {
     load_env<L>(e, cold, k, a.sf, a.si, a.N, i);
   } else {
@@ -235,6 +242,12 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_step(const __grid_constant_
       }
     }
   }
+#ifdef RR_DEBUG_CLOCK
+  last_naughty = (int)((clock64() - dbg_t0) >> 10);  // per-thread elapsed kilo-cycles (debug builds only)
+#endif
+#ifdef RR_DEBUG_COUNT
+  last_naughty = (int)((min(e.dbg[0], 255u) << 24) | (min(e.dbg[1], 255u) << 16) | (min(e.dbg[2], 255u) << 8) | min(e.dbg[3], 255u));
+#endif
   if (live) store_env<L>(e, a.sf, a.si, a.N, i, last_naughty);
   // episode statistics: warp-shuffle reduction, one atomic per warp and statistic
 #pragma unroll

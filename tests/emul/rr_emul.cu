@@ -40,6 +40,7 @@ static void load(E &e, const Consts &k, const double *rob, const double *rhist, 
     e.bvx(b) = p[6]; e.bvy(b) = p[7];
   }
   e.step = step; e.err = 0; e.episode = 0; e.ret_h = e.ret_g = 0;
+  e.invalidate_caches();
 }
 
 template <class E>
