@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_step(const __grid_constant_
   last_naughty = (int)((clock64() - dbg_t0) >> 10);  // per-thread elapsed kilo-cycles (debug builds only)
 #endif
 #ifdef RR_DEBUG_COUNT
-  last_naughty = (int)((min(e.dbg[0], 255u) << 24) | (min(e.dbg[1], 255u) << 16) | (min(e.dbg[2], 255u) << 8) | min(e.dbg[3], 255u));
+  last_naughty = (int)((min(e.dbg[0], 32767u) << 16) | min(e.dbg[2], 65535u));  // slow passes | precise ball-robot tests
 #endif
   if (live) store_env<L>(e, a.sf, a.si, a.N, i, last_naughty);
   // episode statistics: warp-shuffle reduction, one atomic per warp and statistic
