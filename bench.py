@@ -100,7 +100,7 @@ def run_reference(args, rank, world):
         return
     from oracle import rr_oracle
     cores = os.cpu_count() or 1
-    per_core = 1500 if args.preset == "GAME" else 40000  # ~2 s per bench step on each core
+    per_core = 4000 if args.preset == "GAME" else 120000  # ~2 s per bench step on each core
     vals, walls = [], []
     for it in range(args.warmup + args.steps):
         v, wall = rr_oracle.timed_rollout(args.preset, ENV_ID, per_core, cores)
@@ -151,7 +151,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import rr_oracle
         cores = os.cpu_count() or 1
-        per_core = 3000 if args.preset == "GAME" else 80000
+        per_core = 30000 if args.preset == "GAME" else 800000  # ~12 s of CPU work on every core
         v, wall = rr_oracle.timed_rollout(args.preset, ENV_ID, per_core, cores)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"{per_core} random-action env-steps per core on {cores} cores ({wall:.1f} s), "
