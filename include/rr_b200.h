@@ -115,6 +115,16 @@ int rr_max_steps(const rr_sim *s);    /* spec.max_episode_steps = GAME_LENGTH_ST
  * generator (Philox4x32-10, key = seed, counter = (global env index, episode, draw/4)). */
 int rr_reset(rr_sim *s, const uint8_t *mask_dev, void *stream);
 
+/* GameEnv.reset(bln_randomize_pos=False) (RR_EnvBase.py:202-216 -> _set_starting_positions :131-153; caller
+ * main.py:107): back to the stored starting layout.  The layout is _lst_starting_positions: after rr_create it is the
+ * env's own first random placement (:112-113); rr_set_starting_positions replaces it, e.g. with CONFIG_STANDARD
+ * (:35-52).  HOST arrays rob3[N][R][3] = x, y, rot and ball2[N][B][2] = x, y; these two calls synchronise. */
+/* as_constructed != 0 reproduces GameEnv(lst_starting_config) (:112-116): the sprites are first put back to their
+ * freshly constructed state at the origin instead of running on_reset from the current pose. */
+int rr_reset_fixed(rr_sim *s, const uint8_t *mask_dev, int32_t as_constructed, void *stream);
+int rr_set_starting_positions(rr_sim *s, const double *rob3, const double *ball2);
+int rr_get_starting_positions(rr_sim *s, double *rob3, double *ball2);
+
 /* get_game_state(int_team=HAPPY / GRUMPY) of the current state (RR_Observers.py). */
 int rr_observe(rr_sim *s, void *obs_h_dev, void *obs_g_dev, void *stream);
 

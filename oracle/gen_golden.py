@@ -106,7 +106,7 @@ def _put_state(out, i, t, st):
 
 def _obs_dim(env_id, R, B):
     return {"RoboRugby-v0": 0, "RoboRugbySimple-v0": 5, "RoboRugbySimpleDuel-v2": 5,
-            "RoboRugbySimpleDuel-v3": 11}[env_id]
+            "RoboRugbySimpleDuel-v3": 11, "DuelAllCoords": 3 * R + 2 * B}[env_id]
 
 
 # ------------------------------------------------------------------ state builders for `inject`
@@ -456,6 +456,73 @@ def _save(name, out):
     print(f"{name}: {os.path.getsize(path) / 1024:.0f} KiB {meta}", flush=True)
 
 
+def task_reset_fixed(args):
+    """reset(False) records: (state before, starting layout, state after, first observations).
+
+    mode 'own': env built with CONFIG_RANDOM, so the layout is its construction-time placement
+    (RR_EnvBase.py:112-113); mode 'standard' (GAME only): env built with CONFIG_STANDARD (:35-52,114-116),
+    whose record 0 is the freshly constructed state itself (state before = sprites at the origin)."""
+    preset, env_id, mode, seed, n = args
+    import importlib
+    import ref_harness as H
+    const = H.load_reference(preset)
+    from robo_rugby.gym_env.RR_EnvBase import GameEnv
+    random.seed(seed)
+    if mode == "standard":
+        mod, cls = H.ENV_IDS[env_id]
+        H.make_env(env_id)  # seeds the class-level spaces (construction work-around)
+        env = getattr(importlib.import_module(mod), cls)(GameEnv.CONFIG_STANDARD)
+    else:
+        env = H.make_env(env_id)
+    u = env.unwrapped
+    R, B = len(u.lstRobots), len(u.lstBalls)
+    D = _obs_dim(env_id, R, B)
+    out = _empty(n, 1, R, B, R, D)
+    start = np.zeros((n, 3 * R + 2 * B))
+    rng = random.Random(seed)
+    signal.signal(signal.SIGALRM, _alarm)
+    for i in range(n):
+        lay = u._lst_starting_positions
+        start[i, :3 * R] = np.asarray(lay[0], np.float64).reshape(-1)
+        start[i, 3 * R:] = np.asarray(lay[1], np.float64).reshape(-1)
+        if not (mode == "standard" and i == 0):
+            for _ in range(rng.randrange(1, 5)):
+                signal.alarm(10)
+                try:
+                    env.step([rng.randrange(8) for _ in range(R)])
+                except Exception:
+                    break
+                finally:
+                    signal.alarm(0)
+            _put_state(out, i, 0, H.extract(env))
+            env.reset(False)
+        else:
+            out["restart"][i, 0] = 1  # marks "state before = freshly constructed sprites"
+        _put_state(out, i, 1, H.extract(env))
+        oh, og = _obs(env, const.TEAM_HAPPY), _obs(env, const.TEAM_GRUMPY)
+        if oh is not None: out["obs_h"][i, 0] = oh
+        if og is not None: out["obs_g"][i, 0] = og
+    out["start"] = start
+    return args, out
+
+
+def main_extra():
+    """Later additions, generated without touching the files of main(): observer O4 (AllCoords)."""
+    jobs = [(task_rollout, ("GAME", "DuelAllCoords", "chase", 51, 2, 48)),
+            (task_rollout, ("TRAIN", "DuelAllCoords", "chase", 52, 3, 96))]
+    jobs += [(task_reset_fixed, ("GAME", "RoboRugbySimpleDuel-v2", "own", 61, 12)),
+             (task_reset_fixed, ("GAME", "RoboRugbySimpleDuel-v2", "standard", 62, 6)),
+             (task_reset_fixed, ("TRAIN", "RoboRugbySimpleDuel-v2", "own", 63, 16))]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(processes=3, maxtasksperchild=1) as pool:
+        for fn, a in jobs:
+            args, out = pool.apply_async(fn, (a,)).get()
+            if fn is task_reset_fixed:
+                _save(f"{args[0]}_{args[1]}_resetfixed{args[2]}_s{args[3]}", out)
+            else:
+                _save(f"{args[0]}_{args[1]}_{args[2]}_s{args[3]}", out)
+
+
 def main():
     v0, v2, v3, full = "RoboRugbySimple-v0", "RoboRugbySimpleDuel-v2", "RoboRugbySimpleDuel-v3", "RoboRugby-v0"
     jobs = []
@@ -492,4 +559,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "extra":
+        main_extra()
+    else:
+        main()

@@ -52,6 +52,9 @@ SIGNATURES = {
     "rr_obs_dim": (C.c_int, [_vp]),
     "rr_max_steps": (C.c_int, [_vp]),
     "rr_reset": (C.c_int, [_vp, _vp, _vp]),
+    "rr_reset_fixed": (C.c_int, [_vp, _vp, _i32, _vp]),
+    "rr_set_starting_positions": (C.c_int, [_vp, _vp, _vp]),
+    "rr_get_starting_positions": (C.c_int, [_vp, _vp, _vp]),
     "rr_observe": (C.c_int, [_vp, _vp, _vp, _vp]),
     "rr_step": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "rr_step_host": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),

@@ -42,3 +42,20 @@ def get_preset(p):
     if isinstance(p, Preset):
         return p
     return PRESETS[str(p).upper()]
+
+
+def config_standard(preset):
+    """GameEnv.CONFIG_STANDARD (RR_EnvBase.py:32-52) for a preset: ([R x (x, y, rot)], [B x (x, y)]).
+
+    The reference lists 4 robots and 8 balls, so it only fits the GAME entity counts (with TRAIN constants the
+    reference raises "Robot count mismatch", :138-139)."""
+    p = get_preset(preset)
+    W, H = float(p.arena_width), float(p.arena_height)
+    w5, h5 = W / 5, H / 5
+    robots = [(W / 2 + 1 * w5, H - 1 * h5, 135.0), (W / 2 + 2 * w5, H - 2 * h5, 135.0),
+              (W / 2 - 1 * w5, 1 * h5, 315.0), (W / 2 - 2 * w5, 2 * h5, 315.0)]
+    balls = [(w5 * 1, H - h5 * 1), (w5 * 2, H - h5 * 2), (w5 * 3, H - h5 * 3), (w5 * 4, H - h5 * 4),
+             (W / 2, h5), (W / 2, H - h5), (w5, H / 2), (W - w5, H / 2)]
+    if p.num_robots_total != len(robots) or p.num_balls_total != len(balls):
+        raise ValueError(f"Robot count mismatch. {p.num_robots_total} != {len(robots)}.")
+    return robots, balls

@@ -258,7 +258,8 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_step(const __grid_constant_
 }
 
 template <class L>
-__global__ void __launch_bounds__(L::kMaxBlock, 1) k_init(const __grid_constant__ Consts k, double *sf, int32_t *si, int64_t N) {
+__global__ void __launch_bounds__(L::kMaxBlock, 1) k_init(const __grid_constant__ Consts k, double *sf, int32_t *si, int64_t N,
+                                                    double *start) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   typename L::E e;
@@ -269,6 +270,28 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_init(const __grid_constant_
   e.stride = (int)blockDim.x;
   construct_env(e);
   reset_env(e, k, (uint64_t)(k.env_offset + i));
+  record_start(e, start + i, N);  // _lst_starting_positions = _set_random_positions() (RR_EnvBase.py:112-113)
+  store_env<L>(e, sf, si, N, i, 0);
+}
+
+template <class L>
+__global__ void __launch_bounds__(L::kMaxBlock, 1) k_reset_fixed(const __grid_constant__ Consts k, double *sf, int32_t *si,
+                                                           int64_t N, const uint8_t *mask, const double *start,
+                                                           int as_constructed) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  if (mask && !mask[i]) return;
+  typename L::E e;
+  double cold[L::E::kColdDoubles];
+  e.trig = &kSinCosDev[0][0];
+  load_env<L>(e, cold, k, sf, si, N, i);
+  if (as_constructed) {  // GameEnv(lst_starting_config): sprites freshly constructed at the origin (:85-116)
+    const unsigned ep = e.episode;
+    construct_env(e);
+    e.episode = ep;
+  }
+  e.episode += 1;
+  reset_env_fixed(e, k, start + i, N);
   store_env<L>(e, sf, si, N, i, 0);
 }
 
@@ -325,6 +348,7 @@ struct rr_sim {
   int NH, NG, NP, NN, R, B, NF, NI;
   double *sf = nullptr;
   int32_t *si = nullptr;
+  double *start = nullptr;      // [3R + 2B][N] starting layout (_lst_starting_positions)
   double *stats = nullptr;      // where kernels accumulate (own_stats or a caller buffer)
   double *own_stats = nullptr;
   // staging for rr_step_host
@@ -416,7 +440,8 @@ int rr_create(const rr_config *cfg, int64_t n_envs, int device, rr_sim **out) {
   s->R = s->NH + s->NG; s->B = s->NP + s->NN;
   s->NF = s->R * 10 + s->B * 8 + 2;
   s->NI = s->R + 4;
-  if (cudaMalloc(&s->sf, sizeof(double) * s->NF * n_envs) != cudaSuccess ||
+  if (cudaMalloc(&s->start, sizeof(double) * (3 * s->R + 2 * s->B) * n_envs) != cudaSuccess ||
+      cudaMalloc(&s->sf, sizeof(double) * s->NF * n_envs) != cudaSuccess ||
       cudaMalloc(&s->si, sizeof(int32_t) * s->NI * n_envs) != cudaSuccess ||
       cudaMalloc(&s->own_stats, sizeof(double) * RR_NUM_STATS) != cudaSuccess) {
     cudaGetLastError();
@@ -425,7 +450,7 @@ int rr_create(const rr_config *cfg, int64_t n_envs, int device, rr_sim **out) {
   }
   s->stats = s->own_stats;
   CK(cudaMemset(s->stats, 0, sizeof(double) * RR_NUM_STATS));
-  LAUNCH_PRESET(s, (cudaStream_t)0, (k_init<L>), s->k, s->sf, s->si, s->N);
+  LAUNCH_PRESET(s, (cudaStream_t)0, (k_init<L>), s->k, s->sf, s->si, s->N, s->start);
   s->launches++;
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
@@ -436,7 +461,7 @@ int rr_create(const rr_config *cfg, int64_t n_envs, int device, rr_sim **out) {
 int rr_destroy(rr_sim *s) {
   if (!s) return RR_OK;
   cudaSetDevice(s->device);
-  cudaFree(s->sf); cudaFree(s->si); cudaFree(s->own_stats);
+  cudaFree(s->sf); cudaFree(s->si); cudaFree(s->own_stats); cudaFree(s->start);
   cudaFree(s->d_act); cudaFree(s->d_obs_h); cudaFree(s->d_obs_g); cudaFree(s->d_rew); cudaFree(s->d_done);
   delete s;
   return RR_OK;
@@ -465,6 +490,46 @@ int rr_reset(rr_sim *s, const uint8_t *mask_dev, void *stream) {
   LAUNCH_PRESET(s, st, (k_reset<L>), s->k, s->sf, s->si, s->N, mask_dev);
   s->launches++;
   CK(cudaGetLastError());
+  return RR_OK;
+}
+
+int rr_reset_fixed(rr_sim *s, const uint8_t *mask_dev, int32_t as_constructed, void *stream) {
+  if (!s) return fail(RR_E_INVALID, "null handle");
+  CK(cudaSetDevice(s->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  LAUNCH_PRESET(s, st, (k_reset_fixed<L>), s->k, s->sf, s->si, s->N, mask_dev, s->start, (int)as_constructed);
+  s->launches++;
+  CK(cudaGetLastError());
+  return RR_OK;
+}
+
+int rr_set_starting_positions(rr_sim *s, const double *rob3, const double *ball2) {
+  if (!s || !rob3 || !ball2) return fail(RR_E_INVALID, "null argument");
+  CK(cudaSetDevice(s->device));
+  CK(cudaDeviceSynchronize());
+  const int64_t N = s->N;
+  const int R = s->R, B = s->B;
+  std::vector<double> st((size_t)(3 * R + 2 * B) * N);
+  for (int64_t i = 0; i < N; i++) {
+    for (int q = 0; q < 3 * R; q++) st[(size_t)q * N + i] = rob3[i * 3 * R + q];
+    for (int q = 0; q < 2 * B; q++) st[(size_t)(3 * R + q) * N + i] = ball2[i * 2 * B + q];
+  }
+  CK(cudaMemcpy(s->start, st.data(), sizeof(double) * st.size(), cudaMemcpyHostToDevice));
+  return RR_OK;
+}
+
+int rr_get_starting_positions(rr_sim *s, double *rob3, double *ball2) {
+  if (!s || !rob3 || !ball2) return fail(RR_E_INVALID, "null argument");
+  CK(cudaSetDevice(s->device));
+  CK(cudaDeviceSynchronize());
+  const int64_t N = s->N;
+  const int R = s->R, B = s->B;
+  std::vector<double> st((size_t)(3 * R + 2 * B) * N);
+  CK(cudaMemcpy(st.data(), s->start, sizeof(double) * st.size(), cudaMemcpyDeviceToHost));
+  for (int64_t i = 0; i < N; i++) {
+    for (int q = 0; q < 3 * R; q++) rob3[i * 3 * R + q] = st[(size_t)q * N + i];
+    for (int q = 0; q < 2 * B; q++) ball2[i * 2 * B + q] = st[(size_t)(3 * R + q) * N + i];
+  }
   return RR_OK;
 }
 

@@ -89,7 +89,7 @@ class RoboRugbyEnv:
     metadata = {"render.modes": ["human", "rgb_array"], "video.frames_per_second": 30}
     reward_range = (-float("inf"), float("inf"))
 
-    def __init__(self, env_id, preset="GAME", device="cuda:0", seed=0, time_limit=False):
+    def __init__(self, env_id, preset="GAME", device="cuda:0", seed=0, time_limit=False, lst_starting_config=None):
         self.preset = get_preset(preset)
         self.time_limit = bool(time_limit)
         self._v = RoboRugbyVecEnv(env_id, 1, preset=self.preset, device=device, seed=seed, time_limit=time_limit,
@@ -107,6 +107,10 @@ class RoboRugbyEnv:
         self._reward = {TEAM_HAPPY: 0.0, TEAM_GRUMPY: 0.0}
         self._elapsed = 0
         self.np_random = None
+        if lst_starting_config is not None:  # GameEnv(lst_starting_config) (RR_EnvBase.py:112-116)
+            self._v.set_starting_positions(np.asarray(lst_starting_config[0], np.float64),
+                                           np.asarray(lst_starting_config[1], np.float64))
+            self._v.reset_fixed(as_constructed=True)
 
     # -- gym.Env surface -------------------------------------------------------------------
     @property
@@ -124,9 +128,10 @@ class RoboRugbyEnv:
         raise NotImplementedError("rendering is out of scope for the batched simulator (SURVEY.md §2 row 12)")
 
     def reset(self, bln_randomize_pos=True):
-        if not bln_randomize_pos:
-            raise NotImplementedError("fixed-layout reset (CONFIG_STANDARD, RR_EnvBase.py:35-52) is a next-row item")
-        self._v.reset()
+        if bln_randomize_pos:
+            self._v.reset()
+        else:  # back to _lst_starting_positions (RR_EnvBase.py:213-214)
+            self._v.reset_fixed()
         self._elapsed = 0
         self._reward = {TEAM_HAPPY: 0.0, TEAM_GRUMPY: 0.0}
         return self.get_game_state()

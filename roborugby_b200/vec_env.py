@@ -25,7 +25,7 @@ from .constants import ENV_IDS, get_preset
 class RoboRugbyVecEnv:
     def __init__(self, env_id="RoboRugbySimpleDuel-v2", num_envs=4096, preset="GAME", device="cuda:0", seed=0,
                  env_offset=0, time_limit=True, auto_reset=True, out_dtype=torch.float32, strict_reset=False,
-                 n_actions=None):
+                 n_actions=None, observer=None, reward_mask=None):
         if env_id not in ENV_IDS:
             raise ValueError(f"unknown env id {env_id!r}; expected one of {ENV_IDS}")
         if not torch.cuda.is_available():
@@ -42,6 +42,11 @@ class RoboRugbyVecEnv:
         cfg.auto_reset = int(bool(auto_reset))
         cfg.out_f64 = int(out_dtype == torch.float64)
         cfg.strict_reset = int(bool(strict_reset))
+        # class composition a la main.py:42-49: another observer / reward-mixin set on top of the id's defaults
+        if observer is not None:
+            cfg.observer = int(observer)
+        if reward_mask is not None:
+            cfg.reward_mask = int(reward_mask)
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         cfg.env_offset = int(env_offset)
         self.cfg = cfg
@@ -111,6 +116,32 @@ class RoboRugbyVecEnv:
             mp = mask.data_ptr()
         _lib.check(self.lib.rr_reset(self._h, mp, self._stream()))
         return self.observe()[0]
+
+    def reset_fixed(self, mask=None, as_constructed=False):
+        """reset(bln_randomize_pos=False): back to the stored starting layout (the env's first random placement
+        unless set_starting_positions replaced it)."""
+        mp = None
+        if mask is not None:
+            mask = mask.to(self.device, torch.uint8).contiguous()
+            mp = mask.data_ptr()
+        _lib.check(self.lib.rr_reset_fixed(self._h, mp, int(as_constructed), self._stream()))
+        return self.observe()[0]
+
+    def set_starting_positions(self, rob3, ball2):
+        """_lst_starting_positions for every env: rob3 [N, R, 3] (x, y, rot) and ball2 [N, B, 2]; a single layout
+        [R, 3] / [B, 2] (e.g. constants.config_standard(preset)) is broadcast."""
+        N, R, B = self.num_envs, self.num_robots, self.num_balls
+        rob3 = np.ascontiguousarray(np.broadcast_to(np.asarray(rob3, np.float64), (N, R, 3)))
+        ball2 = np.ascontiguousarray(np.broadcast_to(np.asarray(ball2, np.float64), (N, B, 2)))
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        _lib.check(self.lib.rr_set_starting_positions(self._h, p(rob3), p(ball2)))
+
+    def get_starting_positions(self):
+        N, R, B = self.num_envs, self.num_robots, self.num_balls
+        rob3 = np.zeros((N, R, 3)); ball2 = np.zeros((N, B, 2))
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        _lib.check(self.lib.rr_get_starting_positions(self._h, p(rob3), p(ball2)))
+        return rob3, ball2
 
     def observe(self):
         b = self._out(1)

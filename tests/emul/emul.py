@@ -40,6 +40,8 @@ def lib():
         L.emul_reset.restype = C.c_uint
         L.emul_observe.argtypes = [C.POINTER(Config), vp, vp, vp, vp, vp, C.c_int, vp]
         L.emul_observe.restype = C.c_uint
+        L.emul_reset_fixed.argtypes = [C.POINTER(Config), vp, vp, vp, vp, vp, vp, C.c_int]
+        L.emul_reset_fixed.restype = None
         L.emul_use_libm_sincos.argtypes = [C.c_int]
         L.emul_use_libm_sincos.restype = None
         L.emul_sincos.argtypes = [vp, C.c_int, vp, vp]
@@ -83,6 +85,11 @@ class EmulEnv:
     def reset(self, env_index, episode, construct=False):
         return lib().emul_reset(C.byref(self.cfg), _p(self.rob), _p(self.rhist), _p(self.rflag), _p(self.ball),
                                 _p(self.stepc), int(env_index), int(episode), int(construct))
+
+    def reset_fixed(self, start, as_constructed=False):
+        st = np.ascontiguousarray(start, np.float64)
+        lib().emul_reset_fixed(C.byref(self.cfg), _p(self.rob), _p(self.rhist), _p(self.rflag), _p(self.ball),
+                               _p(self.stepc), _p(st), int(as_constructed))
 
     def observe(self, team):
         o = np.full(max(self.obs_dim, 1), np.nan)

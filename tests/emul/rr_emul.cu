@@ -164,5 +164,22 @@ void emul_sincos(const double *x, int n, double *s, double *c) {
 
 // 1: glibc sin/cos (what the oracle uses), 0: rr_sincos_dd (what the GPU uses)
 void emul_use_libm_sincos(int on) { rr::g_host_libm_sincos = on; }
+
+// reset(False) on one env: `start` = R x (x, y, rot) then B x (x, y), contiguous.
+void emul_reset_fixed(const rr_config *cfg, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,
+                      const double *start, int as_constructed) {
+  Consts k = make_consts(*cfg);
+  if (cfg->preset == RR_PRESET_GAME) {
+    HostEnv<2, 2, 4, 4> h;
+    if (as_constructed) construct_env(h.e); else load(h.e, k, rob, rhist, rflag, ball, *step);
+    reset_env_fixed(h.e, k, start, 1);
+    store(h.e, rob, rhist, rflag, ball, step);
+  } else {
+    HostEnv<1, 0, 1, 0> h;
+    if (as_constructed) construct_env(h.e); else load(h.e, k, rob, rhist, rflag, ball, *step);
+    reset_env_fixed(h.e, k, start, 1);
+    store(h.e, rob, rhist, rflag, ball, step);
+  }
+}
 }
 

@@ -9,8 +9,18 @@ STATE_KEYS = ("rob", "rhist", "rflag", "ball", "step")
 
 def parse_name(path):
     """GAME_RoboRugbySimpleDuel-v2_chase_s2.npz -> (preset, env_id, kind)."""
-    m = re.match(r"(GAME|TRAIN)_(RoboRugby[A-Za-z]*-v\d)_([a-z]+)", os.path.basename(path))
+    m = re.match(r"(GAME|TRAIN)_(RoboRugby[A-Za-z]*-v\d|DuelAllCoords)_([a-z]+)", os.path.basename(path))
     return m.group(1), m.group(2), m.group(3)
+
+
+# Ad-hoc class compositions (not registered ids) used by some golden files: base id + observer override.
+OBS_ALLCOORDS = 3
+CUSTOM = {"DuelAllCoords": ("RoboRugbySimpleDuel-v2", OBS_ALLCOORDS)}
+
+
+def resolve_env(env_id):
+    """(registered id to take the default config from, observer override or None)."""
+    return CUSTOM.get(env_id, (env_id, None))
 
 
 def state_at(d, i, t):

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from conftest import golden_files
-from golden_util import actions_at, parse_name, state_at
+from golden_util import actions_at, parse_name, resolve_env, state_at
 from parity_util import compare_record
 
 FILES = [f for f in golden_files("*.npz") if parse_name(f)[2] in ("random", "chase", "sticky", "inject")]
@@ -30,7 +30,10 @@ def _make(path):
     from roborugby_b200 import _lib
     preset, env_id, _ = parse_name(path)
     d = np.load(path)
-    cfg = _lib.default_config(_lib.PRESET_GAME if preset == "GAME" else _lib.PRESET_TRAIN, env_id)
+    base_id, observer = resolve_env(env_id)
+    cfg = _lib.default_config(_lib.PRESET_GAME if preset == "GAME" else _lib.PRESET_TRAIN, base_id)
+    if observer is not None:
+        cfg.observer = observer
     cfg.time_limit = 0
     cfg.auto_reset = 0
     cfg.strict_reset = 1
@@ -82,7 +85,11 @@ def test_kernel_source_matches_oracle_trajectories(oracle, path, trig):
     oracle.scratch_mode(1)
     diverged = 0
     try:
-        o = oracle.OracleEnv(preset, env_id)
+        base_id, observer = resolve_env(env_id)
+        ocfg = oracle.default_config(preset, base_id)
+        if observer is not None:
+            ocfg.observer = observer
+        o = oracle.OracleEnv(cfg=ocfg)
         for i in range(n):
             env.set_state(state_at(d, i, 0)); o.set_state(state_at(d, i, 0))
             for t in range(T):
@@ -188,3 +195,27 @@ def test_fast_rejections_never_contradict_reference_predicates():
             n_fire += v & 1; n_true += (v >> 1) & 1; n_both += (v == 3)
     assert n_both == 0, f"{n_both} pairs rejected although the reference predicate is True"
     assert n_fire > 10000 and n_true > 10000, (n_fire, n_true)  # the sample really straddles the boundary
+
+
+FIXED = golden_files("*_resetfixed*.npz")
+
+
+@pytest.mark.parametrize("path", FIXED, ids=[p.split("/")[-1] for p in FIXED])
+def test_kernel_source_fixed_layout_reset(path, trig):
+    """reset_env_fixed (reset(False) / CONFIG_STANDARD) against the reference's own results."""
+    from golden_util import STATE_KEYS
+    d, cfg, env, preset, env_id = _make(path)
+    for i in range(d["start"].shape[0]):
+        fresh = bool(d["restart"][i, 0])
+        if not fresh:
+            env.set_state(state_at(d, i, 0))
+        env.reset_fixed(d["start"][i], as_constructed=fresh)
+        got, want = env.get_state(), state_at(d, i, 1)
+        for k in ("rflag", "step"):
+            assert np.array_equal(got[k], want[k]), (i, k)
+        for k in ("rob", "ball"):
+            if trig == "libm":
+                assert np.array_equal(got[k], want[k]), (i, k)
+            else:
+                assert np.allclose(got[k], want[k], rtol=0, atol=1e-11), (i, k)
+        assert np.allclose(env.observe(1), d["obs_h"][i, 0], rtol=1e-9, atol=1e-9, equal_nan=True)

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from conftest import golden_files
-from golden_util import actions_at, parse_name, state_at, state_diff, states_equal
+from golden_util import actions_at, parse_name, resolve_env, state_at, state_diff, states_equal
 
 ROLLOUTS = [f for f in golden_files("*.npz") if parse_name(f)[2] in ("random", "chase", "sticky", "inject")]
 
@@ -23,7 +23,11 @@ def test_oracle_matches_reference_bitwise(oracle, path):
     preset, env_id, kind = parse_name(path)
     d = np.load(path)
     n, T = d["act"].shape[:2]
-    env = oracle.OracleEnv(preset, env_id)
+    base_id, observer = resolve_env(env_id)
+    cfg = oracle.default_config(preset, base_id)
+    if observer is not None:
+        cfg.observer = observer
+    env = oracle.OracleEnv(cfg=cfg)
     oracle.scratch_mode(0)
     bad = []
     for mode in ("trajectory", "per_step"):
@@ -86,3 +90,23 @@ def test_oracle_done_semantics(oracle, path):
     # raw env: the step after done raises (RR_EnvBase.py:261-262)
     assert bool(d["raised"]) and env.step([0])["err"] & 1
     assert T == env.cfg.game_length_steps
+
+
+FIXED = golden_files("*_resetfixed*.npz")
+
+
+@pytest.mark.parametrize("path", FIXED, ids=[p.split("/")[-1] for p in FIXED])
+def test_oracle_fixed_layout_reset_matches_reference(oracle, path):
+    """reset(bln_randomize_pos=False) / GameEnv(CONFIG_STANDARD) (RR_EnvBase.py:131-153, :202-216)."""
+    preset, env_id, _ = parse_name(path)
+    d = np.load(path)
+    R, B = d["rob"].shape[2], d["ball"].shape[2]
+    for i in range(d["start"].shape[0]):
+        env = oracle.OracleEnv(preset, env_id)  # freshly constructed sprites at the origin
+        if not d["restart"][i, 0]:
+            env.set_state(state_at(d, i, 0))
+        env.set_starting_positions(d["start"][i, :3 * R].reshape(R, 3), d["start"][i, 3 * R:].reshape(B, 2))
+        assert env.reset_draws([], randomize=False) == 0
+        got, want = env.get_state(), state_at(d, i, 1)
+        assert states_equal(got, want), (i, state_diff(got, want))
+        assert _eq(env.observe(1), d["obs_h"][i, 0]) and _eq(env.observe(-1), d["obs_g"][i, 0])

@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from conftest import golden_files
-from golden_util import STATE_KEYS, parse_name
+from golden_util import STATE_KEYS, parse_name, resolve_env
 from parity_util import compare_record
 
 pytestmark = pytest.mark.gpu
@@ -17,6 +17,9 @@ V2 = "RoboRugbySimpleDuel-v2"
 
 def _venv(env_id, n, preset, **kw):
     from roborugby_b200.vec_env import RoboRugbyVecEnv
+    env_id, observer = resolve_env(env_id)
+    if observer is not None:
+        kw["observer"] = observer
     kw.setdefault("time_limit", False)
     kw.setdefault("auto_reset", False)
     kw.setdefault("out_dtype", torch.float64)
@@ -295,3 +298,45 @@ def test_gpu_gym_wrapper_drop_in():
     assert full.reset() is None and full.action_space.shape == (4,)
     o, r, d, info = full.step([(1.0, 1.0), (0.4, -0.6)])
     assert o is None and r == 0.0
+
+
+FIXED = golden_files("*_resetfixed*.npz")
+
+
+@pytest.mark.parametrize("path", FIXED, ids=[p.split("/")[-1] for p in FIXED])
+def test_gpu_fixed_layout_reset_matches_reference(path):
+    """rr_reset_fixed / rr_set_starting_positions (reset(False), CONFIG_STANDARD) vs the reference's own results."""
+    preset, env_id, _ = parse_name(path)
+    d = np.load(path)
+    n = d["start"].shape[0]
+    R, B = d["rob"].shape[2], d["ball"].shape[2]
+    env = _venv(env_id, n, preset, time_limit=True)
+    own_r, own_b = env.get_starting_positions()
+    st0 = env.get_state()
+    assert np.array_equal(own_r, st0["rob"][:, :, [0, 1, 6]]) and np.array_equal(own_b, st0["ball"][:, :, :2]), \\
+        "after rr_create the stored layout is the env's own first placement"
+    fresh = d["restart"][:, 0].astype(bool)
+    before = {k: d[k][:, 0].copy() for k in STATE_KEYS}
+    env.set_state(before)
+    env.set_starting_positions(d["start"][:, :3 * R].reshape(n, R, 3), d["start"][:, 3 * R:].reshape(n, B, 2))
+    obs = env.reset_fixed(mask=torch.as_tensor(~fresh)).cpu().numpy()
+    if fresh.any():
+        obs_f = env.reset_fixed(mask=torch.as_tensor(fresh), as_constructed=True).cpu().numpy()
+        obs[fresh] = obs_f[fresh]
+    got = env.get_state()
+    for k in ("rflag", "step"):
+        assert np.array_equal(got[k], d[k][:, 1]), k
+    for k in ("rob", "ball"):
+        assert np.allclose(got[k], d[k][:, 1], rtol=0, atol=1e-11), k
+    assert np.array_equal(got["rob"][:, :, [0, 1, 6]], d["rob"][:, 1][:, :, [0, 1, 6]])
+    assert np.allclose(obs, d["obs_h"][:, 0], rtol=1e-9, atol=1e-9, equal_nan=True)
+    # the drop-in wrapper: GameEnv(CONFIG_STANDARD) and reset(False)
+    if preset == "GAME":
+        import roborugby_b200 as rr
+        from roborugby_b200.constants import config_standard
+        e1 = rr.RoboRugbyEnv(env_id, preset="GAME", lst_starting_config=config_standard("GAME"))
+        s1 = e1.get_state()
+        assert np.allclose(s1["rob"][:, [0, 1, 6]], np.asarray(config_standard("GAME")[0]))
+        e1.step([0, 0, 0, 0])
+        e1.reset(False)
+        assert np.allclose(e1.get_state()["ball"][:, :2], np.asarray(config_standard("GAME")[1]))
