@@ -313,7 +313,7 @@ def test_gpu_fixed_layout_reset_matches_reference(path):
     env = _venv(env_id, n, preset, time_limit=True)
     own_r, own_b = env.get_starting_positions()
     st0 = env.get_state()
-    assert np.array_equal(own_r, st0["rob"][:, :, [0, 1, 6]]) and np.array_equal(own_b, st0["ball"][:, :, :2]), \\
+    assert np.array_equal(own_r, st0["rob"][:, :, [0, 1, 6]]) and np.array_equal(own_b, st0["ball"][:, :, :2]), \
         "after rr_create the stored layout is the env's own first placement"
     fresh = d["restart"][:, 0].astype(bool)
     before = {k: d[k][:, 0].copy() for k in STATE_KEYS}
