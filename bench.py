@@ -34,10 +34,10 @@ ENV_ID = "RoboRugbySimpleDuel-v2"
 ENVS_PER_GPU = 65536
 FUSED = 16
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_step launch (65 536 envs x 16 steps) from the committed
-# `ncu --set full` captures profiles/r01_v9_k_step_{game,train}_details.csv; reported as roofline.traffic when the
-# bench runs that exact workload.  (GAME: 131.8 MB read + 616.5 MB written, mostly write-back of the per-thread
-# local arrays; algorithmic bytes are 171 MB.)
-NCU_TRAFFIC_BYTES = {"GAME": 748.3e6, "TRAIN": 49.1e6}
+# `ncu --set full` captures profiles/r01_v11_k_step_{game,train}_by_function.txt (first two lines); reported as
+# roofline.traffic when the bench runs that exact workload.  (GAME: 133.9 MB read + 741.6 MB written, mostly
+# write-back of the per-thread local arrays; algorithmic bytes are 171 MB.)
+NCU_TRAFFIC_BYTES = {"GAME": 875.5e6, "TRAIN": 60.1e6}
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 
@@ -257,7 +257,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (NCU_TRAFFIC_BYTES[args.preset] if (args.envs, args.fused) == (ENVS_PER_GPU, FUSED)
                                      else None),
-                         "traffic_source": "profiles/r01_v9_k_step_%s_details.csv (bytes per launch)" % args.preset.lower(),
+                         "traffic_source": "profiles/r01_v11_k_step_%s_by_function.txt (dram bytes read + written per launch)" % args.preset.lower(),
                          "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src, "bytes_per_env_step": q, "state_bytes": S,
                          "kernel": "rr::k_step<2,2,4,4,float>" if args.preset == "GAME" else "rr::k_step<1,0,1,0,float>",
                          "note": "path is fp64-issue bound, not HBM bound (DESIGN.md §4)"},

@@ -169,6 +169,13 @@ int64_t rr_launch_count(const rr_sim *s);
 /* Bytes of persistent per-env state in HBM (S in DESIGN.md's roofline formula). */
 int64_t rr_state_bytes_per_env(const rr_sim *s);
 
+/* Device self-test of a numeric building block that replaces compiler or libm code on the GPU (no reference
+ * counterpart: the reference uses CPython's float division and libm).  which 0: the branch-free fp64 division
+ * of the contact paths (rr_sim.cuh div_core) against the compiler's division on >= n random operand pairs.
+ * out2[0] = results that differ although the routine reported the operands in range (must be 0),
+ * out2[1] = operand pairs it reported out of range (those are redone with the ordinary division). */
+int rr_selftest(int device, int which, int64_t n, uint64_t seed, int64_t *out2);
+
 #ifdef __cplusplus
 }
 #endif

@@ -68,6 +68,7 @@ SIGNATURES = {
     "rr_set_stats_buffer": (C.c_int, [_vp, _vp]),
     "rr_launch_count": (_i64, [_vp]),
     "rr_state_bytes_per_env": (_i64, [_vp]),
+    "rr_selftest": (C.c_int, [_i32, _i32, _i64, C.c_uint64, _vp]),
 }
 
 _lib = None

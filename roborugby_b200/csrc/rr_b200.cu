@@ -36,7 +36,7 @@ struct Launch {
   using E = Env<NH, NG, NP, NN>;
   // largest block: bounded by 227 KB of shared memory and by 65 536 registers per SM
   static constexpr int kMaxBlock = R > 1 ? 448 : 512;
-  static constexpr int kTrigDoubles = kSinCosRows * 4;  // sin/cos table staged in front of the env fields
+  static constexpr int kTrigDoubles = kTrigRows * 4;  // sin/cos tables staged in front of the env fields
   static constexpr size_t smem_bytes(int block) {
     return sizeof(double) * (kTrigDoubles + E::kDoubles * (size_t)block);
   }
@@ -60,11 +60,11 @@ extern __shared__ double rr_smem[];
 // Stage the sin/cos table in shared memory (all threads of the block; followed by a barrier).
 __device__ __forceinline__ const double *stage_trig_table() {
   const double *src = &kSinCosDev[0][0];
-  for (int q = threadIdx.x; q < kSinCosRows * 4; q += blockDim.x) rr_smem[q] = src[q];
+  for (int q = threadIdx.x; q < kTrigRows * 4; q += blockDim.x) rr_smem[q] = src[q];
   __syncthreads();
   return rr_smem;
 }
-__device__ __forceinline__ double *env_smem_base() { return rr_smem + kSinCosRows * 4 + threadIdx.x; }
+__device__ __forceinline__ double *env_smem_base() { return rr_smem + kTrigRows * 4 + threadIdx.x; }
 
 // HBM column -> (hot shared / cold local) fields.  Robot columns: cx,cy,l,r,t,b,rot,hx,hy,hrot.
 template <class L>
@@ -482,6 +482,73 @@ int rr_obs_dim(const rr_sim *s) {
 }
 int64_t rr_launch_count(const rr_sim *s) { return s ? s->launches : 0; }
 int64_t rr_state_bytes_per_env(const rr_sim *s) { return s ? (int64_t)s->NF * 8 + (int64_t)s->NI * 4 : 0; }
+
+// ---------------------------------------------------------------------------------------------
+// Device self-tests of the numeric building blocks that replace compiler / libm code (tests/test_parity_gpu.py).
+namespace rr {
+__device__ __forceinline__ uint64_t splitmix64(uint64_t &x) {
+  uint64_t z = (x += 0x9E3779B97F4A7C15ull);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+// a double with random sign and mantissa and an exponent drawn from [-span, span]
+__device__ __forceinline__ double random_double(uint64_t &st, int span) {
+  const uint64_t u = splitmix64(st);
+  const int ex = (int)(splitmix64(st) % (uint64_t)(2 * span + 1)) - span;
+  const uint64_t bits = (u & 0x800FFFFFFFFFFFFFull) | ((uint64_t)(1023 + ex) << 52);
+  return __longlong_as_double((long long)bits);
+}
+// which 0: div_core against the compiler's division.  out[0] = cases whose flag said "in range" but whose
+// quotient differs from a / b (must be 0), out[1] = cases flagged out of range (redone by the caller).
+__global__ void k_selftest_div(uint64_t seed, int64_t per_thread, unsigned long long *out) {
+  uint64_t st = seed ^ (0xD1B54A32D192ED03ull * (uint64_t)(blockIdx.x * blockDim.x + threadIdx.x + 1));
+  unsigned long long bad = 0, flagged = 0;
+  for (int64_t it = 0; it < per_thread; it++) {
+    double a, b;
+    switch (it & 3) {
+      case 0: a = random_double(st, 40); b = random_double(st, 40); break;       // slopes, intercepts
+      case 1: a = random_double(st, 1000); b = random_double(st, 1000); break;   // whole exponent range
+      case 2: {  // differences of arena coordinates: multiples of 2^-43 below 1024
+        a = (double)((int64_t)(splitmix64(st) >> 11) - (1ll << 52)) * 0x1p-43;
+        b = (double)((int64_t)(splitmix64(st) >> 11) - (1ll << 52)) * 0x1p-43;
+        break;
+      }
+      default: {  // zeros, subnormals, infinities, NaN now and then
+        const uint64_t sel = splitmix64(st) % 6;
+        a = sel == 0 ? 0.0 : sel == 1 ? 4.9e-324 * (double)(splitmix64(st) % 1000) : random_double(st, 300);
+        b = sel == 2 ? 0.0 : sel == 3 ? HUGE_VAL : sel == 4 ? 1e-310 : sel == 5 ? HUGE_VAL - HUGE_VAL : random_double(st, 300);
+      }
+    }
+    bool ok;
+    const double q = div_core(a, b, ok);
+    const double ref = a / b;
+    if (!ok) flagged++;
+    else if (__double_as_longlong(q) != __double_as_longlong(ref)) bad++;
+  }
+  atomicAdd(&out[0], bad);
+  atomicAdd(&out[1], flagged);
+}
+}  // namespace rr
+
+int rr_selftest(int device, int which, int64_t n, uint64_t seed, int64_t *out2) {
+  if (!out2 || n <= 0) return fail(RR_E_INVALID, "bad selftest arguments");
+  CK(cudaSetDevice(device));
+  unsigned long long *d = nullptr;
+  CK(cudaMalloc(&d, 2 * sizeof(unsigned long long)));
+  CK(cudaMemset(d, 0, 2 * sizeof(unsigned long long)));
+  const int blocks = 148 * 4, threads = 256;
+  const int64_t per_thread = (n + (int64_t)blocks * threads - 1) / ((int64_t)blocks * threads);
+  if (which == 0) rr::k_selftest_div<<<blocks, threads>>>(seed, per_thread, d);
+  else { cudaFree(d); return fail(RR_E_INVALID, "unknown selftest"); }
+  cudaError_t e = cudaDeviceSynchronize();
+  unsigned long long h[2] = {0, 0};
+  if (e == cudaSuccess) e = cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  CK(e);
+  out2[0] = (int64_t)h[0]; out2[1] = (int64_t)h[1];
+  return RR_OK;
+}
 
 int rr_reset(rr_sim *s, const uint8_t *mask_dev, void *stream) {
   if (!s) return fail(RR_E_INVALID, "null handle");

@@ -125,10 +125,17 @@ namespace rr {
   {0x1.6e2b77c40bde1p-1, -0x1.0e729857fad53p-56, 0x1.65dc1fdeb8cbap-1, -0x1.97c1b47337c77p-58}, \
   {0x1.70f451d0a8c40p-1, 0x1.97ede3885770dp-57, 0x1.62fcff20191c7p-1, 0x1.d9143895756efp-57},
 
+#include "rr_sincos_grid.inc"
+
+// One table, two parts: rows [0, kSinCosRows) are sin/cos(i/128) for rr_sincos_dd, rows [kSinCosRows,
+// kSinCosRows + kGridRows) are sin/cos(m * 0.2 degrees) for rr_sincos_grid.  All (hi, lo) pairs.
 constexpr int kSinCosRows = 104;
-static const double kSinCosHost[kSinCosRows][4] = {RR_SINCOS_ROWS};
-__device__ const double kSinCosDev[kSinCosRows][4] = {RR_SINCOS_ROWS};
+constexpr int kGridRows = 450;
+constexpr int kTrigRows = kSinCosRows + kGridRows;
+static const double kSinCosHost[kTrigRows][4] = {RR_SINCOS_ROWS RR_SINCOS_GRID_ROWS};
+__device__ const double kSinCosDev[kTrigRows][4] = {RR_SINCOS_ROWS RR_SINCOS_GRID_ROWS};
 #undef RR_SINCOS_ROWS
+#undef RR_SINCOS_GRID_ROWS
 
 RR_HD __forceinline__ double rr_fma(double a, double b, double c) { return fma(a, b, c); }
 
@@ -202,6 +209,53 @@ RR_HD __noinline__ SinCos rr_sincos_dd(double x, const double *tab) {
   const bool swap = quad & 1;
   const double so = swap ? c : s, co = swap ? s : c;
   // quad 0: (s, c)  1: (c, -s)  2: (-s, -c)  3: (-c, s)
+  out.s = (quad & 2) ? -so : so;
+  out.c = (quad == 1 || quad == 2) ? -co : co;
+  return out;
+}
+
+// The simulator's arguments are not arbitrary: every angle is a robot heading (an integer number of degrees
+// at reset, then +-0.6 / +-1.2 per frame), +-90, +45 or 360 minus it, i.e. g = N * 0.2 degrees up to the
+// rounding drift d of those additions (|d| ~ 1e-13 rad after a whole episode).  For such x = g + d
+//   sin x = S + [C d - S d^2/2],  cos x = C - [S d + C d^2/2]        (S, C = sin g, cos g from the table)
+// needs no polynomial and no pi/2 reduction: N = rint(x * 900/pi), d = x - N * pi/900 in double-double
+// (pi/900 = c1 + c2 + c3, N * c1 exact), N = 450 * quadrant + m.  The leading product is kept exact with an
+// fma like in rr_sincos_dd, so the value before the final rounding carries ~2^-100 relative error and the
+// result is the correctly rounded one (d^3/6 < 2^-110 is dropped: the fast path requires |d| < 2^-36).
+// Anything else (|x| >= 16, an angle off the grid) goes to rr_sincos_dd: same contract, same bits on host
+// and GPU.  profiles/README.md v11: rr_sincos_dd was 33 % of all executed instructions.
+RR_HD __noinline__ SinCos rr_sincos_grid(double x, const double *tab) {
+  const double fn = rint(x * RR_GRID_INV_STEP);
+  const double t = rr_fma(-fn, RR_GRID_C1, x);  // exact: fn * c1 fits 53 bits and is within a factor 2 of x
+  const double q = fn * RR_GRID_C2;
+  const double dh = t - q;
+  if (!(fabs(x) < 16.0) || !(fabs(dh) < 0x1p-36)) return rr_sincos_dd(x, tab);
+  const double bv = dh - t;  // TwoSum(t, -q)
+  const double dl = ((t - (dh - bv)) + (-q - bv)) - rr_fma(fn, RR_GRID_C3, rr_fma(fn, RR_GRID_C2, -q));
+  const int Np = (int)fn + 12 * kGridRows;  // |fn| <= 4584 for |x| < 16: positive dividend, quadrant unchanged
+  const int qd = Np / kGridRows, m = Np - qd * kGridRows;
+  const double *row = tab + 4 * (kSinCosRows + m);
+  const double Sh = row[0], Sl = row[1], Ch = row[2], Cl = row[3];
+  const double h2 = 0.5 * (dh * dh);
+  double s, c;
+  {
+    const double p = Ch * dh, pe = rr_fma(Ch, dh, -p);
+    const double a = Sh + p;
+    const double b = (Sh - a) + p;  // Fast2Sum: |Sh| >= sin(0.2 deg) >> |p|, or Sh == 0 (exact)
+    const double rest = rr_fma(-Sh, h2, rr_fma(Ch, dl, rr_fma(Cl, dh, Sl)));
+    s = a + ((b + pe) + rest);
+  }
+  {
+    const double p = Sh * dh, pe = rr_fma(Sh, dh, -p);
+    const double a = Ch - p;
+    const double b = (Ch - a) - p;  // |Ch| >= cos(89.8 deg) >> |p|
+    const double rest = rr_fma(-Ch, h2, rr_fma(-Sh, dl, rr_fma(-Sl, dh, Cl)));
+    c = a + ((b - pe) + rest);
+  }
+  const int quad = qd & 3;
+  const bool swap = quad & 1;
+  const double so = swap ? c : s, co = swap ? s : c;
+  SinCos out;
   out.s = (quad & 2) ? -so : so;
   out.c = (quad == 1 || quad == 2) ? -co : co;
   return out;

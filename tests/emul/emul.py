@@ -46,6 +46,8 @@ def lib():
         L.emul_use_libm_sincos.restype = None
         L.emul_sincos.argtypes = [vp, C.c_int, vp, vp]
         L.emul_sincos.restype = None
+        L.emul_sincos2.argtypes = [vp, C.c_int, vp, vp, C.c_int]
+        L.emul_sincos2.restype = None
         L.emul_predicates.argtypes = [C.POINTER(Config), vp, vp, vp, vp, vp, vp, vp]
         L.emul_predicates.restype = None
         _lib = L
@@ -108,10 +110,11 @@ def predicates(cfg, st):
     return rr, br
 
 
-def sincos(x):
+def sincos(x, dd_only=False):
+    """The simulator's sin/cos on the host: rr_sincos_grid (grid fast path + rr_sincos_dd), or rr_sincos_dd alone."""
     x = np.ascontiguousarray(x, np.float64)
     s = np.empty_like(x); c = np.empty_like(x)
-    lib().emul_sincos(_p(x), x.size, _p(s), _p(c))
+    lib().emul_sincos2(_p(x), x.size, _p(s), _p(c), int(bool(dd_only)))
     return s, c
 
 

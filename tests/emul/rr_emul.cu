@@ -157,10 +157,15 @@ void emul_predicates(const rr_config *cfg, double *rob, double *rhist, int32_t *
       br_out[b * 4 + r] = (ball_clear_of_robot(e, b, r) ? 1 : 0) | (ball_robot_collided(e, k, b, r, err) ? 2 : 0);
 }
 
-// n evaluations of the simulator's sin/cos routine (rr_sincos.cuh) on the host.
-void emul_sincos(const double *x, int n, double *s, double *c) {
-  for (int i = 0; i < n; i++) { SinCos r = rr_sincos_dd(x[i], &kSinCosHost[0][0]); s[i] = r.s; c[i] = r.c; }
+// n evaluations of the simulator's sin/cos routine (rr_sincos.cuh) on the host.  which 0: rr_sincos_grid (what
+// the kernels call: grid fast path, rr_sincos_dd for everything else), 1: rr_sincos_dd alone.
+void emul_sincos2(const double *x, int n, double *s, double *c, int which) {
+  for (int i = 0; i < n; i++) {
+    SinCos r = which ? rr_sincos_dd(x[i], &kSinCosHost[0][0]) : rr_sincos_grid(x[i], &kSinCosHost[0][0]);
+    s[i] = r.s; c[i] = r.c;
+  }
 }
+void emul_sincos(const double *x, int n, double *s, double *c) { emul_sincos2(x, n, s, c, 0); }
 
 // 1: glibc sin/cos (what the oracle uses), 0: rr_sincos_dd (what the GPU uses)
 void emul_use_libm_sincos(int on) { rr::g_host_libm_sincos = on; }

@@ -340,3 +340,18 @@ def test_gpu_fixed_layout_reset_matches_reference(path):
         e1.step([0, 0, 0, 0])
         e1.reset(False)
         assert np.allclose(e1.get_state()["ball"][:, :2], np.asarray(config_standard("GAME")[1]))
+
+
+def test_gpu_division_core_is_the_correctly_rounded_quotient():
+    """rr_sim.cuh div_core (the branch-free division the contact paths batch) against the compiler's division:
+    every quotient it reports as in range must be bit-identical; the rest is redone by the caller."""
+    import ctypes as C
+    import numpy as np
+    from roborugby_b200 import _lib
+    lib = _lib.load()
+    out = np.zeros(2, np.int64)
+    n = 400_000_000
+    rc = lib.rr_selftest(0, 0, n, 20261018, out.ctypes.data_as(C.c_void_p))
+    assert rc == 0, lib.rr_last_error()
+    assert out[0] == 0, f"{out[0]} quotients differ from a / b"
+    assert 0 < out[1] < 0.4 * n          # the out-of-range classes of the generator, and only those
