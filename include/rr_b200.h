@@ -42,6 +42,22 @@ extern "C" {
 #define RR_REW_CHASE 1u   /* ChasePosBall :46-66         */
 #define RR_REW_PUSHPOS 2u /* PushPosBallsToGoal :138-157 */
 #define RR_REW_NAUGHTY 4u /* NaughtyBots :112-135        */
+#define RR_REW_DONTDRIVE 8u        /* DontDriveInGoals :69-83 (robot_in_goal RR_TrashyPhysics.py:12-15) */
+#define RR_REW_KEEPMOVING 16u      /* KeepMovingGuys :86-98       */
+#define RR_REW_BASEDESTRUCTION 32u /* BaseDestruction :101-111 (adds nothing: goals are never destroyed on the live path) */
+#define RR_REW_PUSHNEG 64u         /* PushNegBallsFromGoal :160-179 */
+/* ids for rr_config.reward_order: the sequence in which the on_step_end bodies run, one id per nibble, low nibble
+ * first, 0 ends.  Each on_step_end calls super() before adding its own terms, so the bodies run in REVERSE MRO
+ * order, and NaughtyBots.on_step_end does not call super(): mixins listed after it in the class never run.
+ * reward_order == 0 selects Naughty, Chase, PushPos, PushNeg, BaseDestruction, DontDrive, KeepMoving (those in the
+ * mask), which is the order of the registered ids (RR_Environments.py:11-37). */
+#define RR_MIX_CHASE 1u
+#define RR_MIX_PUSHPOS 2u
+#define RR_MIX_NAUGHTY 3u
+#define RR_MIX_DONTDRIVE 4u
+#define RR_MIX_KEEPMOVING 5u
+#define RR_MIX_BASEDESTRUCTION 6u
+#define RR_MIX_PUSHNEG 7u
 
 /* observers, RR_Observers.py */
 #define RR_OBS_NONE 0
@@ -88,7 +104,7 @@ typedef struct rr_config {
   int32_t strict_reset; /* 1: reference placement test verbatim (may leave two balls exactly 14 px
                            apart, a state in which the reference itself never returns);
                            0: additionally reject such ball pairs */
-  int32_t reserved;
+  uint32_t reward_order; /* RR_MIX_* sequence (see above); 0 = canonical order of the mixins in reward_mask */
   uint64_t seed;        /* Philox key */
   int64_t env_offset;   /* global index of this handle's env 0 (rank * n_envs when sharded) */
 } rr_config;

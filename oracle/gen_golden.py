@@ -106,7 +106,7 @@ def _put_state(out, i, t, st):
 
 def _obs_dim(env_id, R, B):
     return {"RoboRugby-v0": 0, "RoboRugbySimple-v0": 5, "RoboRugbySimpleDuel-v2": 5,
-            "RoboRugbySimpleDuel-v3": 11, "DuelAllCoords": 3 * R + 2 * B}[env_id]
+            "RoboRugbySimpleDuel-v3": 11, "DuelAllCoords": 3 * R + 2 * B, "DuelAllMixins": 5, "DuelCutChain": 5}[env_id]
 
 
 # ------------------------------------------------------------------ state builders for `inject`
@@ -249,6 +249,8 @@ def task_rollout(args):
     R, B = len(u.lstRobots), len(u.lstBalls)
     discrete = env_id != "RoboRugby-v0"
     n_act = 1 if env_id == "RoboRugbySimple-v0" else R
+    if kind == "partial":   # only the happy robots are driven: the others keep zero thrust and never move (KeepMovingGuys)
+        n_act = max(1, R // 2)
     A = R if discrete else 2 * R
     D = _obs_dim(env_id, R, B)
     out = _empty(n, T, R, B, A, D)
@@ -523,6 +525,20 @@ def main_extra():
                 _save(f"{args[0]}_{args[1]}_{args[2]}_s{args[3]}", out)
 
 
+def main_mixins():
+    """§8f rank 2: the remaining reward mixins (DontDriveInGoals, KeepMovingGuys, BaseDestruction, PushNegBallsFromGoal)
+    in two ad-hoc compositions (ref_harness.MIXIN_COMPOSITIONS), random / chase / partially driven rollouts."""
+    jobs = [("GAME", "DuelAllMixins", "chase", 71, 3, 64), ("GAME", "DuelAllMixins", "partial", 72, 3, 48),
+            ("GAME", "DuelCutChain", "partial", 73, 3, 48), ("TRAIN", "DuelAllMixins", "random", 74, 6, 96),
+            ("TRAIN", "DuelCutChain", "chase", 75, 4, 96)]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(processes=5, maxtasksperchild=1) as pool:
+        res = [pool.apply_async(task_rollout, (a,)) for a in jobs]
+        for r in res:
+            args, out = r.get()
+            _save(f"{args[0]}_{args[1]}_{args[2]}_s{args[3]}", out)
+
+
 def main():
     v0, v2, v3, full = "RoboRugbySimple-v0", "RoboRugbySimpleDuel-v2", "RoboRugbySimpleDuel-v3", "RoboRugby-v0"
     jobs = []
@@ -561,5 +577,7 @@ def main():
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "extra":
         main_extra()
+    elif len(sys.argv) > 1 and sys.argv[1] == "mixins":
+        main_mixins()
     else:
         main()

@@ -79,13 +79,22 @@ def load_reference(preset):
     return const
 
 
+# must stay identical to tests/golden_util.py CUSTOM_MIXINS (the tests translate the same lists into a config)
+MIXIN_COMPOSITIONS = {
+    "DuelAllMixins": ["KeepMovingGuys", "DontDriveInGoals", "BaseDestruction", "PushNegBallsFromGoal",
+                      "PushPosBallsToGoal", "ChasePosBall", "NaughtyBots"],
+    "DuelCutChain": ["DontDriveInGoals", "ChasePosBall", "NaughtyBots", "KeepMovingGuys"],
+}
+
+
 def make_env(env_id, through_gym=False):
     """Construct a reference env.  through_gym=True returns the TimeLimit-wrapped env."""
     import gym
     import numpy as np
     from robo_rugby.gym_env.RR_EnvBase import GameEnv
     const = importlib.import_module("robo_rugby.gym_env.RR_Constants")
-    if env_id in ("RoboRugbySimple-v0", "RoboRugbySimpleDuel-v2") and GameEnv.observation_space is None:
+    if (env_id in ("RoboRugbySimple-v0", "RoboRugbySimpleDuel-v2") or env_id in MIXIN_COMPOSITIONS) \
+            and GameEnv.observation_space is None:
         hi = max(const.ARENA_WIDTH, const.ARENA_HEIGHT, 360)
         GameEnv.observation_space = gym.spaces.Box(-hi, hi, dtype=np.float32, shape=(5,))
     if env_id == "DuelAllCoords":
@@ -99,6 +108,15 @@ def make_env(env_id, through_gym=False):
             pass
 
         env = DuelAllCoords()
+        env.spec = gym.spec("RoboRugbySimpleDuel-v2")
+        return env
+    if env_id in MIXIN_COMPOSITIONS:
+        # ad-hoc reward-mixin compositions (class-definition order) on SimpleDuel2's observer and action space
+        import robo_rugby.gym_env.RR_ScoreKeepers as sk
+        import robo_rugby.gym_env.RR_Observers as obs
+        import robo_rugby.gym_env.RR_EnvBase as base
+        bases = tuple(getattr(sk, n) for n in MIXIN_COMPOSITIONS[env_id]) + (obs.PosBall_BasicLidar, base.GameEnv_Simple)
+        env = type(env_id, bases, {})()
         env.spec = gym.spec("RoboRugbySimpleDuel-v2")
         return env
     if through_gym:

@@ -30,6 +30,18 @@ extern "C" {
 #define RRO_REW_CHASE 1u    /* ChasePosBall        :46-66   */
 #define RRO_REW_PUSHPOS 2u  /* PushPosBallsToGoal  :138-157 */
 #define RRO_REW_NAUGHTY 4u  /* NaughtyBots         :112-135 */
+#define RRO_REW_DONTDRIVE 8u        /* DontDriveInGoals     :69-83   */
+#define RRO_REW_KEEPMOVING 16u      /* KeepMovingGuys       :86-98   */
+#define RRO_REW_BASEDESTRUCTION 32u /* BaseDestruction      :101-111 */
+#define RRO_REW_PUSHNEG 64u         /* PushNegBallsFromGoal :160-179 */
+/* on_step_end execution sequence (reward_order): one id per nibble, low nibble first, 0 ends */
+#define RRO_MIX_CHASE 1u
+#define RRO_MIX_PUSHPOS 2u
+#define RRO_MIX_NAUGHTY 3u
+#define RRO_MIX_DONTDRIVE 4u
+#define RRO_MIX_KEEPMOVING 5u
+#define RRO_MIX_BASEDESTRUCTION 6u
+#define RRO_MIX_PUSHNEG 7u
 
 /* observers (RR_Observers.py) */
 #define RRO_OBS_NONE 0
@@ -57,6 +69,9 @@ typedef struct {
   int observer;              /* RRO_OBS_*             */
   int discrete;              /* 1: GameEnv_Simple.step (RR_EnvBase.py:617-626) */
   int time_limit;            /* 1: gym TimeLimit semantics (done at step >= T), 0: raw (step > T) */
+  uint32_t reward_order;     /* RRO_MIX_* sequence in which the on_step_end bodies execute: reverse MRO order, cut at
+                                NaughtyBots, whose on_step_end does not call super() (RR_ScoreKeepers.py:130-135);
+                                0 = Naughty, Chase, PushPos, PushNeg, BaseDestruction, DontDrive, KeepMoving */
 } rro_config;
 
 typedef struct rro_env rro_env;

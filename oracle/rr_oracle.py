@@ -28,7 +28,7 @@ class Config(C.Structure):
         ("n_pos", C.c_int), ("n_neg", C.c_int),
         ("game_length_steps", C.c_int), ("game_mode", C.c_int),
         ("reward_mask", C.c_uint32), ("observer", C.c_int),
-        ("discrete", C.c_int), ("time_limit", C.c_int),
+        ("discrete", C.c_int), ("time_limit", C.c_int), ("reward_order", C.c_uint32),
     ]
 
 

@@ -35,7 +35,7 @@ class Config(C.Structure):
         ("abi_version", C.c_int32), ("preset", C.c_int32), ("reward_mask", C.c_uint32),
         ("observer", C.c_int32), ("discrete", C.c_int32), ("time_limit", C.c_int32),
         ("auto_reset", C.c_int32), ("out_f64", C.c_int32), ("strict_reset", C.c_int32),
-        ("reserved", C.c_int32), ("seed", C.c_uint64), ("env_offset", C.c_int64),
+        ("reward_order", C.c_uint32), ("seed", C.c_uint64), ("env_offset", C.c_int64),
     ]
 
 

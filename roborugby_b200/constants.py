@@ -59,3 +59,33 @@ def config_standard(preset):
     if p.num_robots_total != len(robots) or p.num_balls_total != len(balls):
         raise ValueError(f"Robot count mismatch. {p.num_robots_total} != {len(robots)}.")
     return robots, balls
+
+
+# Reward mixins (RR_ScoreKeepers.py): name -> (rr_config.reward_mask bit RR_REW_*, rr_config.reward_order id RR_MIX_*)
+REWARD_MIXINS = {
+    "ChasePosBall": (1, 1), "PushPosBallsToGoal": (2, 2), "NaughtyBots": (4, 3), "DontDriveInGoals": (8, 4),
+    "KeepMovingGuys": (16, 5), "BaseDestruction": (32, 6), "PushNegBallsFromGoal": (64, 7),
+}
+
+
+def reward_config_from_mixins(mixins):
+    """(reward_mask, reward_order) for a class composed as `class Env(*mixins, Observer, GameEnv_Simple)`.
+
+    Every on_step_end calls super() first and then adds its own terms, so the bodies execute in reverse MRO order;
+    NaughtyBots.on_step_end (RR_ScoreKeepers.py:130-135) does not call super(), so the mixins listed AFTER it never
+    run theirs (their on_step_begin hooks still do, which is why they stay in the mask)."""
+    mask, chain = 0, []
+    for name in mixins:
+        if name not in REWARD_MIXINS:
+            raise ValueError(f"unknown reward mixin {name!r}; expected one of {sorted(REWARD_MIXINS)}")
+        mask |= REWARD_MIXINS[name][0]
+    for name in mixins:           # MRO order; the chain of super() calls stops at NaughtyBots
+        chain.append(name)
+        if name == "NaughtyBots":
+            break
+    order = 0
+    for n, name in enumerate(reversed(chain)):
+        order |= REWARD_MIXINS[name][1] << (4 * n)
+    if len(chain) > 8:
+        raise ValueError("at most 8 mixins")
+    return mask, order

@@ -89,11 +89,15 @@ class RoboRugbyEnv:
     metadata = {"render.modes": ["human", "rgb_array"], "video.frames_per_second": 30}
     reward_range = (-float("inf"), float("inf"))
 
-    def __init__(self, env_id, preset="GAME", device="cuda:0", seed=0, time_limit=False, lst_starting_config=None):
+    def __init__(self, env_id, preset="GAME", device="cuda:0", seed=0, time_limit=False, lst_starting_config=None,
+                 reward_mixins=None, observer=None):
+        """reward_mixins: names of RR_ScoreKeepers.py mixins in class-definition order, composed on top of `env_id`'s
+        observer and action space the way main.py:42-49 composes ad-hoc classes (None: the id's own mixins)."""
         self.preset = get_preset(preset)
         self.time_limit = bool(time_limit)
         self._v = RoboRugbyVecEnv(env_id, 1, preset=self.preset, device=device, seed=seed, time_limit=time_limit,
-                                  auto_reset=False, out_dtype=torch.float64, strict_reset=True)
+                                  auto_reset=False, out_dtype=torch.float64, strict_reset=True,
+                                  reward_mixins=reward_mixins, observer=observer)
         self.spec = EnvSpec(env_id, self._v.max_episode_steps)
         R = self._v.num_robots
         if self._v.discrete:

@@ -25,7 +25,7 @@ from .constants import ENV_IDS, get_preset
 class RoboRugbyVecEnv:
     def __init__(self, env_id="RoboRugbySimpleDuel-v2", num_envs=4096, preset="GAME", device="cuda:0", seed=0,
                  env_offset=0, time_limit=True, auto_reset=True, out_dtype=torch.float32, strict_reset=False,
-                 n_actions=None, observer=None, reward_mask=None):
+                 n_actions=None, observer=None, reward_mask=None, reward_order=None, reward_mixins=None):
         if env_id not in ENV_IDS:
             raise ValueError(f"unknown env id {env_id!r}; expected one of {ENV_IDS}")
         if not torch.cuda.is_available():
@@ -45,8 +45,14 @@ class RoboRugbyVecEnv:
         # class composition a la main.py:42-49: another observer / reward-mixin set on top of the id's defaults
         if observer is not None:
             cfg.observer = int(observer)
+        if reward_mixins is not None:   # class-definition order, e.g. ("KeepMovingGuys", "ChasePosBall", "NaughtyBots")
+            from .constants import reward_config_from_mixins
+            reward_mask, reward_order = reward_config_from_mixins(reward_mixins)
         if reward_mask is not None:
             cfg.reward_mask = int(reward_mask)
+            cfg.reward_order = 0
+        if reward_order is not None:
+            cfg.reward_order = int(reward_order)
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         cfg.env_offset = int(env_offset)
         self.cfg = cfg

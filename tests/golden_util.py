@@ -9,18 +9,48 @@ STATE_KEYS = ("rob", "rhist", "rflag", "ball", "step")
 
 def parse_name(path):
     """GAME_RoboRugbySimpleDuel-v2_chase_s2.npz -> (preset, env_id, kind)."""
-    m = re.match(r"(GAME|TRAIN)_(RoboRugby[A-Za-z]*-v\d|DuelAllCoords)_([a-z]+)", os.path.basename(path))
+    m = re.match(r"(GAME|TRAIN)_(RoboRugby[A-Za-z]*-v\d|DuelAllCoords|DuelAllMixins|DuelCutChain)_([a-z]+)", os.path.basename(path))
     return m.group(1), m.group(2), m.group(3)
 
 
 # Ad-hoc class compositions (not registered ids) used by some golden files: base id + observer override.
 OBS_ALLCOORDS = 3
 CUSTOM = {"DuelAllCoords": ("RoboRugbySimpleDuel-v2", OBS_ALLCOORDS)}
+# ... and reward-mixin compositions, in class-definition order (oracle/ref_harness.py builds exactly these classes)
+CUSTOM_MIXINS = {
+    "DuelAllMixins": ("RoboRugbySimpleDuel-v2", ["KeepMovingGuys", "DontDriveInGoals", "BaseDestruction", "PushNegBallsFromGoal",
+                                                 "PushPosBallsToGoal", "ChasePosBall", "NaughtyBots"]),
+    # NaughtyBots.on_step_end does not call super(): KeepMovingGuys, listed after it, never runs its on_step_end
+    "DuelCutChain": ("RoboRugbySimpleDuel-v2", ["DontDriveInGoals", "ChasePosBall", "NaughtyBots", "KeepMovingGuys"]),
+}
 
 
 def resolve_env(env_id):
     """(registered id to take the default config from, observer override or None)."""
+    if env_id in CUSTOM_MIXINS:
+        return CUSTOM_MIXINS[env_id][0], None
     return CUSTOM.get(env_id, (env_id, None))
+
+
+def resolve_rewards(env_id):
+    """(reward_mask, reward_order) override of an ad-hoc mixin composition, or None for registered ids."""
+    if env_id not in CUSTOM_MIXINS:
+        return None
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), ".."))
+    from roborugby_b200.constants import reward_config_from_mixins
+    return reward_config_from_mixins(CUSTOM_MIXINS[env_id][1])
+
+
+def apply_overrides(cfg, env_id):
+    """Observer / reward-mixin overrides of an ad-hoc composition onto a config struct (oracle or C ABI)."""
+    _, observer = resolve_env(env_id)
+    if observer is not None:
+        cfg.observer = observer
+    rw = resolve_rewards(env_id)
+    if rw is not None:
+        cfg.reward_mask, cfg.reward_order = rw
+    return cfg
 
 
 def state_at(d, i, t):

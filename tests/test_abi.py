@@ -59,3 +59,17 @@ def test_create_fails_loudly_without_gpu():
     import roborugby_b200
     with pytest.raises(RuntimeError):
         roborugby_b200.RoboRugbyVecEnv("RoboRugbySimpleDuel-v2", 8)
+
+
+def test_reward_mixin_composition_to_config():
+    """Host logic: class-definition order of RR_ScoreKeepers.py mixins -> (reward_mask, reward_order).  The bodies of
+    on_step_end run in reverse MRO order and NaughtyBots ends the chain (it does not call super())."""
+    from roborugby_b200.constants import reward_config_from_mixins as f
+    # the registered ids' own composition (RR_Environments.py:11-37): Naughty, Chase, PushPos
+    assert f(["PushPosBallsToGoal", "ChasePosBall", "NaughtyBots"]) == (7, 0x213)
+    # mixins after NaughtyBots keep their mask bit (on_step_begin still runs) but never execute on_step_end
+    assert f(["DontDriveInGoals", "ChasePosBall", "NaughtyBots", "KeepMovingGuys"]) == (8 | 1 | 4 | 16, 0x413)
+    assert f(["KeepMovingGuys"]) == (16, 0x5)
+    import pytest
+    with pytest.raises(ValueError):
+        f(["NoSuchMixin"])

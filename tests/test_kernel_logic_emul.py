@@ -9,10 +9,10 @@ import numpy as np
 import pytest
 
 from conftest import golden_files
-from golden_util import actions_at, parse_name, resolve_env, state_at
+from golden_util import actions_at, apply_overrides, parse_name, resolve_env, state_at
 from parity_util import compare_record
 
-FILES = [f for f in golden_files("*.npz") if parse_name(f)[2] in ("random", "chase", "sticky", "inject")]
+FILES = [f for f in golden_files("*.npz") if parse_name(f)[2] in ("random", "chase", "sticky", "inject", "partial")]
 
 
 @pytest.fixture(params=["libm", "dd"])
@@ -31,9 +31,7 @@ def _make(path):
     preset, env_id, _ = parse_name(path)
     d = np.load(path)
     base_id, observer = resolve_env(env_id)
-    cfg = _lib.default_config(_lib.PRESET_GAME if preset == "GAME" else _lib.PRESET_TRAIN, base_id)
-    if observer is not None:
-        cfg.observer = observer
+    cfg = apply_overrides(_lib.default_config(_lib.PRESET_GAME if preset == "GAME" else _lib.PRESET_TRAIN, base_id), env_id)
     cfg.time_limit = 0
     cfg.auto_reset = 0
     cfg.strict_reset = 1
@@ -86,9 +84,7 @@ def test_kernel_source_matches_oracle_trajectories(oracle, path, trig):
     diverged = 0
     try:
         base_id, observer = resolve_env(env_id)
-        ocfg = oracle.default_config(preset, base_id)
-        if observer is not None:
-            ocfg.observer = observer
+        ocfg = apply_overrides(oracle.default_config(preset, base_id), env_id)
         o = oracle.OracleEnv(cfg=ocfg)
         for i in range(n):
             env.set_state(state_at(d, i, 0)); o.set_state(state_at(d, i, 0))

@@ -9,9 +9,9 @@ import numpy as np
 import pytest
 
 from conftest import golden_files
-from golden_util import actions_at, parse_name, resolve_env, state_at, state_diff, states_equal
+from golden_util import actions_at, apply_overrides, parse_name, resolve_env, state_at, state_diff, states_equal
 
-ROLLOUTS = [f for f in golden_files("*.npz") if parse_name(f)[2] in ("random", "chase", "sticky", "inject")]
+ROLLOUTS = [f for f in golden_files("*.npz") if parse_name(f)[2] in ("random", "chase", "sticky", "inject", "partial")]
 
 
 def _eq(a, b):
@@ -24,9 +24,7 @@ def test_oracle_matches_reference_bitwise(oracle, path):
     d = np.load(path)
     n, T = d["act"].shape[:2]
     base_id, observer = resolve_env(env_id)
-    cfg = oracle.default_config(preset, base_id)
-    if observer is not None:
-        cfg.observer = observer
+    cfg = apply_overrides(oracle.default_config(preset, base_id), env_id)
     env = oracle.OracleEnv(cfg=cfg)
     oracle.scratch_mode(0)
     bad = []

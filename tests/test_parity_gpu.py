@@ -5,21 +5,24 @@ import numpy as np
 import pytest
 
 from conftest import golden_files
-from golden_util import STATE_KEYS, parse_name, resolve_env
+from golden_util import STATE_KEYS, parse_name, resolve_env, resolve_rewards
 from parity_util import compare_record
 
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
-FILES = [f for f in golden_files("*.npz") if parse_name(f)[2] in ("random", "chase", "sticky", "inject")]
+FILES = [f for f in golden_files("*.npz") if parse_name(f)[2] in ("random", "chase", "sticky", "inject", "partial")]
 V2 = "RoboRugbySimpleDuel-v2"
 
 
 def _venv(env_id, n, preset, **kw):
     from roborugby_b200.vec_env import RoboRugbyVecEnv
+    rewards = resolve_rewards(env_id)
     env_id, observer = resolve_env(env_id)
     if observer is not None:
         kw["observer"] = observer
+    if rewards is not None:
+        kw["reward_mask"], kw["reward_order"] = rewards
     kw.setdefault("time_limit", False)
     kw.setdefault("auto_reset", False)
     kw.setdefault("out_dtype", torch.float64)
