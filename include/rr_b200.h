@@ -152,7 +152,9 @@ int rr_step(rr_sim *s, const void *actions_dev, int32_t n_actions, int32_t k_ste
 
 /* Same call with HOST buffers: copies actions host->device, launches, copies results back and
  * synchronises the stream before returning.  This is what a single-process caller of the
- * reference's env.step() would bind. */
+ * reference's env.step() would bind.  Where the copies dominate (TRAIN preset) the k steps run as
+ * up to four launches whose result rows travel while the next launch computes; results are
+ * identical to one launch.  Pinned host buffers are needed for the copies to be asynchronous. */
 int rr_step_host(rr_sim *s, const void *actions_host, int32_t n_actions, int32_t k_steps,
                  void *obs_h_host, void *obs_g_host, void *rew_host, uint8_t *done_host, void *stream);
 

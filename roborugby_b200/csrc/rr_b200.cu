@@ -355,6 +355,8 @@ struct rr_sim {
   void *d_act = nullptr, *d_obs_h = nullptr, *d_obs_g = nullptr, *d_rew = nullptr;
   uint8_t *d_done = nullptr;
   size_t cap_act = 0, cap_obs_h = 0, cap_obs_g = 0, cap_rew = 0, cap_done = 0;
+  cudaStream_t copy_stream = nullptr;  // rr_step_host: results of one chunk of steps travel while the next chunk runs
+  cudaEvent_t chunk_done[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t launches = 0;
 };
 
@@ -463,6 +465,9 @@ int rr_destroy(rr_sim *s) {
   cudaSetDevice(s->device);
   cudaFree(s->sf); cudaFree(s->si); cudaFree(s->own_stats); cudaFree(s->start);
   cudaFree(s->d_act); cudaFree(s->d_obs_h); cudaFree(s->d_obs_g); cudaFree(s->d_rew); cudaFree(s->d_done);
+  if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+  for (cudaEvent_t e : s->chunk_done)
+    if (e) cudaEventDestroy(e);
   delete s;
   return RR_OK;
 }
@@ -670,15 +675,43 @@ int rr_step_host(rr_sim *s, const void *actions, int32_t n_actions, int32_t k_st
   if ((rc = ensure(&s->d_obs_g, &s->cap_obs_g, obs_b ? obs_b : 1))) return rc;
   if ((rc = ensure(&s->d_rew, &s->cap_rew, rew_b))) return rc;
   if ((rc = ensure((void **)&s->d_done, &s->cap_done, done_b))) return rc;
+  if (!s->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t &e : s->chunk_done) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
   if (act_b) CK(cudaMemcpyAsync(s->d_act, actions, act_b, cudaMemcpyHostToDevice, st));
-  rc = rr_step(s, s->d_act, n_actions, k_steps, obs_h ? s->d_obs_h : nullptr, obs_g ? s->d_obs_g : nullptr,
-               rew ? s->d_rew : nullptr, done ? s->d_done : nullptr, stream);
-  if (rc) return rc;
-  if (obs_h && obs_b) CK(cudaMemcpyAsync(obs_h, s->d_obs_h, obs_b, cudaMemcpyDeviceToHost, st));
-  if (obs_g && obs_b) CK(cudaMemcpyAsync(obs_g, s->d_obs_g, obs_b, cudaMemcpyDeviceToHost, st));
-  if (rew) CK(cudaMemcpyAsync(rew, s->d_rew, rew_b, cudaMemcpyDeviceToHost, st));
-  if (done) CK(cudaMemcpyAsync(done, s->d_done, done_b, cudaMemcpyDeviceToHost, st));
+  // The K steps run as up to four launches of K/4 steps (same results: the state lives in HBM between launches);
+  // the device-to-host copies of one chunk's rows overlap the next chunk's kernel.  Outputs are [K][N][...], so a
+  // chunk of steps is one contiguous range of every buffer.
+  // Every launch pays a fixed cost (state load / store, corner tables) and ends with its slowest env, so splitting
+  // only pays where the copies dominate: 4 chunks for the light TRAIN preset (294 -> 345 M env-steps/s end to end),
+  // 1 for GAME (66.9 M; 2 chunks 63.5 M, 4 chunks 59.0 M: profiles/README.md).  RR_HOST_CHUNKS overrides it.
+  int chunks = s->R > 1 ? 1 : 4;
+  if (const char *ev = getenv("RR_HOST_CHUNKS")) chunks = atoi(ev);
+  if (chunks > 4) chunks = 4;
+  if (chunks < 1 || k_steps < chunks) chunks = 1;
+  const size_t act_row = (size_t)s->N * n_actions * (s->cfg.discrete ? 1 : 4);
+  const size_t obs_row = (size_t)s->N * rr_obs_dim(s) * osz, rew_row = (size_t)s->N * 2 * osz, done_row = (size_t)s->N;
+  int k0 = 0;
+  for (int c = 0; c < chunks; c++) {
+    const int kc = (k_steps - k0) / (chunks - c);
+    const size_t r0 = (size_t)k0, rn = (size_t)kc;
+    rc = rr_step(s, (const char *)s->d_act + r0 * act_row, n_actions, kc, obs_h ? (char *)s->d_obs_h + r0 * obs_row : nullptr,
+                 obs_g ? (char *)s->d_obs_g + r0 * obs_row : nullptr, rew ? (char *)s->d_rew + r0 * rew_row : nullptr,
+                 done ? s->d_done + r0 * done_row : nullptr, stream);
+    if (rc) return rc;
+    CK(cudaEventRecord(s->chunk_done[c], st));
+    CK(cudaStreamWaitEvent(s->copy_stream, s->chunk_done[c], 0));
+    cudaStream_t cs = s->copy_stream;
+    if (obs_h && obs_row) CK(cudaMemcpyAsync((char *)obs_h + r0 * obs_row, (char *)s->d_obs_h + r0 * obs_row, rn * obs_row, cudaMemcpyDeviceToHost, cs));
+    if (obs_g && obs_row) CK(cudaMemcpyAsync((char *)obs_g + r0 * obs_row, (char *)s->d_obs_g + r0 * obs_row, rn * obs_row, cudaMemcpyDeviceToHost, cs));
+    if (rew) CK(cudaMemcpyAsync((char *)rew + r0 * rew_row, (char *)s->d_rew + r0 * rew_row, rn * rew_row, cudaMemcpyDeviceToHost, cs));
+    if (done) CK(cudaMemcpyAsync(done + r0 * done_row, s->d_done + r0 * done_row, rn * done_row, cudaMemcpyDeviceToHost, cs));
+    k0 += kc;
+  }
+  CK(cudaStreamSynchronize(s->copy_stream));
   CK(cudaStreamSynchronize(st));
+  (void)obs_b; (void)rew_b; (void)done_b;
   return RR_OK;
 }
 
