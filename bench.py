@@ -5,8 +5,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 Workload (BASELINE.json configs[2]): RoboRugbySimpleDuel-v2, 65 536 envs per GPU, shipped (GAME)
-constants, uniformly random discrete actions for all four robots, fused launches of 16 env-steps
-with in-kernel auto-reset.  One bench "step" = one fused launch = 65 536 x 16 env-steps per GPU.
+constants, uniformly random discrete actions for all four robots, fused launches of 32 env-steps
+with in-kernel auto-reset.  One bench "step" = one fused launch = 65 536 x 32 env-steps per GPU.
 
   value    whole-job env-steps/s, inputs (actions) already resident in HBM, CUDA-event timed,
            max over ranks, L2 flushed between timed launches
@@ -32,12 +32,13 @@ sys.path.insert(0, ROOT)
 
 ENV_ID = "RoboRugbySimpleDuel-v2"
 ENVS_PER_GPU = 65536
-FUSED = 16
+FUSED = 32
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_step launch (65 536 envs x 16 steps) from the committed
-# `ncu --set full` captures profiles/r01_v11_k_step_{game,train}_by_function.txt (first two lines); reported as
-# roofline.traffic when the bench runs that exact workload.  (GAME: 133.9 MB read + 741.6 MB written, mostly
-# write-back of the per-thread local arrays; algorithmic bytes are 171 MB.)
-NCU_TRAFFIC_BYTES = {"GAME": 875.5e6, "TRAIN": 60.1e6}
+# `ncu --set full` captures profiles/r01_v12_k_step_{game,train}_by_function.txt (first two lines); reported as
+# roofline.traffic when the bench runs that exact workload.  (GAME: 189.7 MB read + 1435.6 MB written, mostly
+# write-back of the per-thread local arrays, whose 217 MB footprint exceeds the 126 MB L2; algorithmic bytes are
+# 226 MB.)
+NCU_TRAFFIC_BYTES = {"GAME": 1625.3e6, "TRAIN": 138.5e6}
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 
@@ -257,7 +258,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (NCU_TRAFFIC_BYTES[args.preset] if (args.envs, args.fused) == (ENVS_PER_GPU, FUSED)
                                      else None),
-                         "traffic_source": "profiles/r01_v11_k_step_%s_by_function.txt (dram bytes read + written per launch)" % args.preset.lower(),
+                         "traffic_source": "profiles/r01_v12_k_step_%s_by_function.txt (dram bytes read + written per launch)" % args.preset.lower(),
                          "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src, "bytes_per_env_step": q, "state_bytes": S,
                          "kernel": "rr::k_step<2,2,4,4,float>" if args.preset == "GAME" else "rr::k_step<1,0,1,0,float>",
                          "note": "path is fp64-issue bound, not HBM bound (DESIGN.md §4)"},
