@@ -106,7 +106,8 @@ def _put_state(out, i, t, st):
 
 def _obs_dim(env_id, R, B):
     return {"RoboRugby-v0": 0, "RoboRugbySimple-v0": 5, "RoboRugbySimpleDuel-v2": 5,
-            "RoboRugbySimpleDuel-v3": 11, "DuelAllCoords": 3 * R + 2 * B, "DuelAllMixins": 5, "DuelCutChain": 5}[env_id]
+            "RoboRugbySimpleDuel-v3": 11, "DuelAllCoords": 3 * R + 2 * B, "DuelAllMixins": 5, "DuelCutChain": 5,
+            "DuelAllCoordsPrior": 6 * R + 4 * B}[env_id]
 
 
 # ------------------------------------------------------------------ state builders for `inject`
@@ -531,6 +532,8 @@ def main_mixins():
     jobs = [("GAME", "DuelAllMixins", "chase", 71, 3, 64), ("GAME", "DuelAllMixins", "partial", 72, 3, 48),
             ("GAME", "DuelCutChain", "partial", 73, 3, 48), ("TRAIN", "DuelAllMixins", "random", 74, 6, 96),
             ("TRAIN", "DuelCutChain", "chase", 75, 4, 96)]
+    if len(sys.argv) > 2 and sys.argv[2] == "prior":   # the AllCoords_WithPrior observer, added afterwards
+        jobs = [("GAME", "DuelAllCoordsPrior", "chase", 81, 2, 48), ("TRAIN", "DuelAllCoordsPrior", "random", 82, 3, 96)]
     ctx = mp.get_context("spawn")
     with ctx.Pool(processes=5, maxtasksperchild=1) as pool:
         res = [pool.apply_async(task_rollout, (a,)) for a in jobs]

@@ -97,6 +97,19 @@ def make_env(env_id, through_gym=False):
             and GameEnv.observation_space is None:
         hi = max(const.ARENA_WIDTH, const.ARENA_HEIGHT, 360)
         GameEnv.observation_space = gym.spaces.Box(-hi, hi, dtype=np.float32, shape=(5,))
+    if env_id == "DuelAllCoordsPrior":
+        # SimpleDuel2's reward mixins with the AllCoords_WithPrior observer (RR_Observers.py:86-110)
+        import robo_rugby.gym_env.RR_ScoreKeepers as sk
+        import robo_rugby.gym_env.RR_Observers as obs
+        import robo_rugby.gym_env.RR_EnvBase as base
+
+        class DuelAllCoordsPrior(sk.PushPosBallsToGoal, sk.ChasePosBall, sk.NaughtyBots, obs.AllCoords_WithPrior,
+                                 base.GameEnv_Simple):
+            pass
+
+        env = DuelAllCoordsPrior()
+        env.spec = gym.spec("RoboRugbySimpleDuel-v2")
+        return env
     if env_id == "DuelAllCoords":
         # Not a registered id: SimpleDuel2's reward mixins composed with the AllCoords observer
         # (RR_Observers.py:47-83), the way main.py:42-49 composes ad-hoc classes.  Exercises observer O4.

@@ -48,6 +48,7 @@ extern "C" {
 #define RRO_OBS_BASIC_LIDAR 1 /* PosBall_BasicLidar      :116-166, 5 values  */
 #define RRO_OBS_LIDAR6_V2 2   /* SingleBall_6wayLidar_v2 :287-406, 11 values */
 #define RRO_OBS_ALLCOORDS 3   /* AllCoords               :47-83, 3R+2B values */
+#define RRO_OBS_ALLCOORDS_PRIOR 4 /* AllCoords_WithPrior :86-110, 6R+4B values */
 
 /* error bits: the Python exceptions of the path */
 #define RRO_ERR_STEP_AFTER_DONE 1u      /* RR_EnvBase.py:261-262 */

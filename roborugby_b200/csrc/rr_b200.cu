@@ -42,7 +42,10 @@ struct Launch {
   }
   // HBM structure-of-arrays layout
   static constexpr int kRobotF = 10, kBallF = 8;
-  static constexpr int NF = R * kRobotF + B * kBallF + 2;
+  // + the rectDblPriorStep poses (3 per robot, 2 per ball) behind the episode returns: allocated always, loaded and
+  // stored only by handles whose observer reports them (RR_OBS_ALLCOORDS_PRIOR)
+  static constexpr int NF_BASE = R * kRobotF + B * kBallF + 2;
+  static constexpr int NF = NF_BASE + 3 * R + 2 * B;
   static constexpr int NI = R + 4;
 };
 
@@ -98,14 +101,23 @@ __device__ __forceinline__ void load_env(typename L::E &e, double *cold, const C
     f += L::kBallF;
   }
   e.ret_h = sf[(f + 0) * N + i]; e.ret_g = sf[(f + 1) * N + i];
+  f += 2;
+  if (k.observer == RR_OBS_ALLCOORDS_PRIOR) {
+#pragma unroll 1
+    for (int r = 0; r < L::R; r++, f += 3) {
+      e.rc(r, 13) = sf[(f + 0) * N + i]; e.rc(r, 14) = sf[(f + 1) * N + i]; e.rc(r, 15) = sf[(f + 2) * N + i];
+    }
+#pragma unroll 1
+    for (int b = 0; b < L::B; b++, f += 2) { e.bf(b, 8) = sf[(f + 0) * N + i]; e.bf(b, 9) = sf[(f + 1) * N + i]; }
+  }
   e.step = si[(L::R + 0) * N + i];
   e.episode = (unsigned)si[(L::R + 1) * N + i];
   e.err = (unsigned)si[(L::R + 2) * N + i];
 }
 
 template <class L>
-__device__ __forceinline__ void store_env(const typename L::E &e, double *__restrict__ sf, int32_t *__restrict__ si,
-                                          int64_t N, int64_t i, int last_naughty) {
+__device__ __forceinline__ void store_env(const typename L::E &e, const Consts &k, double *__restrict__ sf,
+                                          int32_t *__restrict__ si, int64_t N, int64_t i, int last_naughty) {
   int f = 0;
 #pragma unroll 1
   for (int r = 0; r < L::R; r++) {
@@ -123,6 +135,15 @@ __device__ __forceinline__ void store_env(const typename L::E &e, double *__rest
     f += L::kBallF;
   }
   sf[(f + 0) * N + i] = e.ret_h; sf[(f + 1) * N + i] = e.ret_g;
+  f += 2;
+  if (k.observer == RR_OBS_ALLCOORDS_PRIOR) {
+#pragma unroll 1
+    for (int r = 0; r < L::R; r++, f += 3) {
+      sf[(f + 0) * N + i] = e.rc(r, 13); sf[(f + 1) * N + i] = e.rc(r, 14); sf[(f + 2) * N + i] = e.rc(r, 15);
+    }
+#pragma unroll 1
+    for (int b = 0; b < L::B; b++, f += 2) { sf[(f + 0) * N + i] = e.bf(b, 8); sf[(f + 1) * N + i] = e.bf(b, 9); }
+  }
   si[(L::R + 0) * N + i] = e.step;
   si[(L::R + 1) * N + i] = (int32_t)e.episode;
   si[(L::R + 2) * N + i] = (int32_t)e.err;
@@ -248,7 +269,7 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_step(const __grid_constant_
 #ifdef RR_DEBUG_COUNT
   last_naughty = (int)((min(e.dbg[0], 32767u) << 16) | min(e.dbg[2], 65535u));  // slow passes | precise ball-robot tests
 #endif
-  if (live) store_env<L>(e, a.sf, a.si, a.N, i, last_naughty);
+  if (live) store_env<L>(e, k, a.sf, a.si, a.N, i, last_naughty);
   // episode statistics: warp-shuffle reduction, one atomic per warp and statistic
 #pragma unroll
   for (int q = 0; q < RR_NUM_STATS; q++) {
@@ -271,7 +292,7 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_init(const __grid_constant_
   construct_env(e);
   reset_env(e, k, (uint64_t)(k.env_offset + i));
   record_start(e, start + i, N);  // _lst_starting_positions = _set_random_positions() (RR_EnvBase.py:112-113)
-  store_env<L>(e, sf, si, N, i, 0);
+  store_env<L>(e, k, sf, si, N, i, 0);
 }
 
 template <class L>
@@ -292,7 +313,7 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_reset_fixed(const __grid_co
   }
   e.episode += 1;
   reset_env_fixed(e, k, start + i, N);
-  store_env<L>(e, sf, si, N, i, 0);
+  store_env<L>(e, k, sf, si, N, i, 0);
 }
 
 template <class L>
@@ -307,7 +328,7 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_reset(const __grid_constant
   load_env<L>(e, cold, k, sf, si, N, i);
   e.episode += 1;
   reset_env(e, k, (uint64_t)(k.env_offset + i));
-  store_env<L>(e, sf, si, N, i, 0);
+  store_env<L>(e, k, sf, si, N, i, 0);
 }
 
 template <class L, typename OutT>
@@ -418,11 +439,16 @@ using LTrain = Launch<1, 0, 1, 0>;
     }                                                                                                       \
   } while (0)
 
+// columns of sf behind the base state: rectDblPriorStep poses, kept only for the observer that reports them
+static inline int prior_columns(const rr_sim *s) {
+  return s->cfg.observer == RR_OBS_ALLCOORDS_PRIOR ? 3 * s->R + 2 * s->B : 0;
+}
+
 int rr_create(const rr_config *cfg, int64_t n_envs, int device, rr_sim **out) {
   if (!cfg || !out || n_envs <= 0) return fail(RR_E_INVALID, "bad arguments");
   if (cfg->abi_version != RR_ABI_VERSION) return fail(RR_E_INVALID, "abi_version mismatch");
   if (cfg->preset != RR_PRESET_GAME && cfg->preset != RR_PRESET_TRAIN) return fail(RR_E_INVALID, "unknown preset");
-  if (cfg->observer < 0 || cfg->observer > RR_OBS_ALLCOORDS) return fail(RR_E_INVALID, "unknown observer");
+  if (cfg->observer < 0 || cfg->observer > RR_OBS_ALLCOORDS_PRIOR) return fail(RR_E_INVALID, "unknown observer");
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if (ce != cudaSuccess || ndev == 0)
@@ -443,7 +469,7 @@ int rr_create(const rr_config *cfg, int64_t n_envs, int device, rr_sim **out) {
   s->NF = s->R * 10 + s->B * 8 + 2;
   s->NI = s->R + 4;
   if (cudaMalloc(&s->start, sizeof(double) * (3 * s->R + 2 * s->B) * n_envs) != cudaSuccess ||
-      cudaMalloc(&s->sf, sizeof(double) * s->NF * n_envs) != cudaSuccess ||
+      cudaMalloc(&s->sf, sizeof(double) * (s->NF + prior_columns(s)) * n_envs) != cudaSuccess ||
       cudaMalloc(&s->si, sizeof(int32_t) * s->NI * n_envs) != cudaSuccess ||
       cudaMalloc(&s->own_stats, sizeof(double) * RR_NUM_STATS) != cudaSuccess) {
     cudaGetLastError();
@@ -482,11 +508,14 @@ int rr_obs_dim(const rr_sim *s) {
     case RR_OBS_BASIC_LIDAR: return 5;
     case RR_OBS_LIDAR6_V2: return 11;
     case RR_OBS_ALLCOORDS: return 3 * s->R + 2 * s->B;
+    case RR_OBS_ALLCOORDS_PRIOR: return 6 * s->R + 4 * s->B;
     default: return 0;
   }
 }
 int64_t rr_launch_count(const rr_sim *s) { return s ? s->launches : 0; }
-int64_t rr_state_bytes_per_env(const rr_sim *s) { return s ? (int64_t)s->NF * 8 + (int64_t)s->NI * 4 : 0; }
+int64_t rr_state_bytes_per_env(const rr_sim *s) {
+  return s ? (int64_t)(s->NF + prior_columns(s)) * 8 + (int64_t)s->NI * 4 : 0;
+}
 
 // ---------------------------------------------------------------------------------------------
 // Device self-tests of the numeric building blocks that replace compiler / libm code (tests/test_parity_gpu.py).

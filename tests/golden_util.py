@@ -9,13 +9,15 @@ STATE_KEYS = ("rob", "rhist", "rflag", "ball", "step")
 
 def parse_name(path):
     """GAME_RoboRugbySimpleDuel-v2_chase_s2.npz -> (preset, env_id, kind)."""
-    m = re.match(r"(GAME|TRAIN)_(RoboRugby[A-Za-z]*-v\d|DuelAllCoords|DuelAllMixins|DuelCutChain)_([a-z]+)", os.path.basename(path))
+    m = re.match(r"(GAME|TRAIN)_(RoboRugby[A-Za-z]*-v\d|DuelAllCoordsPrior|DuelAllCoords|DuelAllMixins|DuelCutChain)_([a-z]+)", os.path.basename(path))
     return m.group(1), m.group(2), m.group(3)
 
 
 # Ad-hoc class compositions (not registered ids) used by some golden files: base id + observer override.
 OBS_ALLCOORDS = 3
-CUSTOM = {"DuelAllCoords": ("RoboRugbySimpleDuel-v2", OBS_ALLCOORDS)}
+OBS_ALLCOORDS_PRIOR = 4
+CUSTOM = {"DuelAllCoords": ("RoboRugbySimpleDuel-v2", OBS_ALLCOORDS),
+          "DuelAllCoordsPrior": ("RoboRugbySimpleDuel-v2", OBS_ALLCOORDS_PRIOR)}
 # ... and reward-mixin compositions, in class-definition order (oracle/ref_harness.py builds exactly these classes)
 CUSTOM_MIXINS = {
     "DuelAllMixins": ("RoboRugbySimpleDuel-v2", ["KeepMovingGuys", "DontDriveInGoals", "BaseDestruction", "PushNegBallsFromGoal",

@@ -358,3 +358,39 @@ def test_gpu_division_core_is_the_correctly_rounded_quotient():
     assert rc == 0, lib.rr_last_error()
     assert out[0] == 0, f"{out[0]} quotients differ from a / b"
     assert 0 < out[1] < 0.4 * n          # the out-of-range classes of the generator, and only those
+
+
+def test_gpu_allcoords_with_prior_across_reset_matches_oracle(oracle):
+    """AllCoords_WithPrior (RR_Observers.py:86-110) reports rectDblPriorStep, which on_reset copies BEFORE the new
+    positions are drawn: the first observation of an episode shows the previous episode's last pose.  Steps, an
+    explicit reset (a separate launch: the prior poses live in HBM), and the observation of both teams vs the oracle."""
+    N, seed, K = 48, 11, 3
+    env = _venv(V2, N, "GAME", seed=seed, observer=4, time_limit=True, auto_reset=False)
+    assert env.obs_dim == 6 * env.num_robots + 4 * env.num_balls
+    g = torch.Generator().manual_seed(3)
+    acts = torch.randint(0, 8, (K, N, env.num_robots), generator=g, dtype=torch.uint8)
+    obs_h, obs_g, _, _ = (x.cpu().numpy() for x in env.step_k(acts.cuda(), K))
+    first_h = env.reset().cpu().numpy().copy()
+    first_g = env.observe()[1].cpu().numpy().copy()
+    oracle.scratch_mode(1)
+    try:
+        for i in range(N):
+            cfg = oracle.default_config("GAME", V2)
+            cfg.observer = 4
+            cfg.time_limit = 1
+            o = oracle.OracleEnv(cfg=cfg)
+            o.reset_philox(seed, i, 0)
+            for s in range(K):
+                out = o.step(acts[s, i].numpy())
+                assert np.allclose(out["obs_h"], obs_h[s, i], rtol=1e-9, atol=1e-9), (i, s)
+                assert np.allclose(out["obs_g"], obs_g[s, i], rtol=1e-9, atol=1e-9), (i, s)
+            before = o.get_state()["rob"][:, :2].copy()
+            o.reset_philox(seed, i, 1)
+            want_h, want_g = o.observe(1), o.observe(-1)
+            assert np.allclose(want_h, first_h[i], rtol=1e-9, atol=1e-9), i
+            assert np.allclose(want_g, first_g[i], rtol=1e-9, atol=1e-9), i
+            # the prior pose of robot 0 in the first observation is where the previous episode left it
+            assert np.allclose(first_h[i][3:5], before[0], rtol=0, atol=1e-9) and not np.allclose(first_h[i][0:2], before[0])
+    finally:
+        oracle.scratch_mode(0)
+    env.close()
