@@ -13,6 +13,9 @@ def __getattr__(name):  # torch-dependent modules are imported lazily
     if name in ("RoboRugbyVecEnv",):
         from .vec_env import RoboRugbyVecEnv
         return RoboRugbyVecEnv
+    if name in ("og_twitchy_actions",):
+        from .players import og_twitchy_actions
+        return og_twitchy_actions
     if name in ("make", "spec", "RoboRugbyEnv", "DebugInfo"):
         from . import gym_env
         return getattr(gym_env, name)

@@ -85,3 +85,16 @@ def test_dqn_loop_runs_on_gpu_vec_env():
     assert out["env_steps"] == 40 * 512 and out["env_steps_per_s"] > 0
     assert ag.mem_cntr == 40 * 512 and all(l == l for l in out["losses"])  # finite
     assert out["stats"]["steps"] == 40 * 512
+
+
+def test_og_twitchy_action_distribution():
+    """Batched OG_Twitchy (RR_Players.py:14-30): 5 % left, 45 % forward, 45 % back, 5 % right, as GameEnv_Simple ids."""
+    import torch
+    from roborugby_b200.players import og_twitchy_actions
+    g = torch.Generator().manual_seed(0)
+    a = og_twitchy_actions((200000, 2), device="cpu", generator=g)
+    assert a.dtype == torch.uint8 and a.shape == (200000, 2)
+    frac = torch.bincount(a.flatten().long(), minlength=8).double() / a.numel()
+    # ids: 0 forward (1,1), 1 back (-1,-1), 2 left (-1,1), 3 right (1,-1)   (RR_EnvBase.py:593-602)
+    assert abs(frac[2] - 0.05) < 0.004 and abs(frac[0] - 0.45) < 0.006
+    assert abs(frac[1] - 0.45) < 0.006 and abs(frac[3] - 0.05) < 0.004 and frac[4:].sum() == 0
