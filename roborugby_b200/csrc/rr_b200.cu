@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_step(const __grid_constant_
         n_cmd = A;
         uint32_t w = 0;
         if (A == 4) {  // one coalesced 32-bit load per env
-          w = *(const uint32_t *)ap;
+          w = __ldcs((const uint32_t *)ap);  // streamed once: keep the L2 for the per-thread local arrays
         } else {
 #pragma unroll 1
           for (int r = 0; r < A; r++) w |= (uint32_t)ap[r] << (8 * r);
@@ -246,8 +246,10 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_step(const __grid_constant_
           reset_env(e, k, (uint64_t)(k.env_offset + i));
         }
       }
-      if (a.rew) { ((OutT *)a.rew)[row * 2] = (OutT)o.rew_h; ((OutT *)a.rew)[row * 2 + 1] = (OutT)o.rew_g; }
-      if (a.done) a.done[row] = (uint8_t)done;
+      // results are written once and never read by this launch: streaming stores (evict-first) so that 100 MB of
+      // them per launch do not push the per-thread local arrays out of the L2
+      if (a.rew) { __stcs(&((OutT *)a.rew)[row * 2], (OutT)o.rew_h); __stcs(&((OutT *)a.rew)[row * 2 + 1], (OutT)o.rew_g); }
+      if (a.done) __stcs(&a.done[row], (unsigned char)done);
       if (dim > 0 && (a.obs_h || a.obs_g)) {
         double ob[kMaxObs];
         unsigned oerr = 0;
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_step(const __grid_constant_
           observe(e, k, team, ob, oerr);
           dst += row * dim;
 #pragma unroll 1
-          for (int q = 0; q < dim; q++) dst[q] = (OutT)ob[q];
+          for (int q = 0; q < dim; q++) __stcs(&dst[q], (OutT)ob[q]);
         }
       }
     }
