@@ -104,7 +104,7 @@ def run_reference(args, rank, world):
     per_core = 4000 if args.preset == "GAME" else 120000  # ~2 s per bench step on each core
     vals, walls = [], []
     for it in range(args.warmup + args.steps):
-        v, wall = rr_oracle.timed_rollout(args.preset, ENV_ID, per_core, cores)
+        v, wall = rr_oracle.timed_rollout(args.preset, args.env_id, per_core, cores)
         if it >= args.warmup:
             vals.append(v); walls.append(wall)
     value = sum(vals) / len(vals)
@@ -121,9 +121,10 @@ def run_reference(args, rank, world):
 
 
 def workload_config(args, world):
-    return {"workload": f"{ENV_ID} {args.preset} preset, {args.envs} envs/GPU x {world} GPU, random discrete actions, "
-                        f"{args.fused} fused env-steps per launch, auto-reset (BASELINE configs[2])",
-            "env_id": ENV_ID, "preset": args.preset, "envs_per_gpu": args.envs, "fused_steps": args.fused,
+    return {"workload": f"{args.env_id} {args.preset} preset, {args.envs} envs/GPU x {world} GPU, random "
+                        f"{'continuous thrust' if args.env_id == 'RoboRugby-v0' else 'discrete'} actions, "
+                        f"{args.fused} fused env-steps per launch, auto-reset (BASELINE configs[{3 if args.env_id == 'RoboRugby-v0' else 2}])",
+            "env_id": args.env_id, "preset": args.preset, "envs_per_gpu": args.envs, "fused_steps": args.fused,
             "parallelism": f"env-shard x{world} (no data-path collective)", "l2": "flushed between timed launches"}
 
 
@@ -136,6 +137,8 @@ def main():
     ap.add_argument("--preset", default="GAME", choices=["GAME", "TRAIN"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--fused", type=int, default=FUSED)
+    ap.add_argument("--env-id", default=ENV_ID, help="another registered id, e.g. RoboRugby-v0 (the full game: continuous "
+                    "thrust pairs for all robots, BASELINE configs[3]); the default is the workload the metric is quoted on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -153,7 +156,7 @@ def main():
         from oracle import rr_oracle
         cores = os.cpu_count() or 1
         per_core = 30000 if args.preset == "GAME" else 800000  # ~12 s of CPU work on every core
-        v, wall = rr_oracle.timed_rollout(args.preset, ENV_ID, per_core, cores)
+        v, wall = rr_oracle.timed_rollout(args.preset, args.env_id, per_core, cores)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"{per_core} random-action env-steps per core on {cores} cores ({wall:.1f} s), "
                                   f"C oracle port of the reference algorithm, same env id and preset"}
@@ -173,12 +176,16 @@ def main():
     N, K = args.envs, args.fused
     total = N * world
     n_local, offset = shard_envs(total, rank, world)
-    env = RoboRugbyVecEnv(ENV_ID, n_local, preset=args.preset, device=dev, seed=2026, env_offset=offset,
+    env = RoboRugbyVecEnv(args.env_id, n_local, preset=args.preset, device=dev, seed=2026, env_offset=offset,
                           time_limit=True, auto_reset=True, out_dtype=torch.float32)
     R, D = env.num_robots, env.obs_dim
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     n_sets = 4  # rotate pre-generated action sets so consecutive launches differ
-    acts = [torch.randint(0, 8, (K, n_local, R), generator=g, dtype=torch.uint8, device=dev) for _ in range(n_sets)]
+    if env.discrete:
+        A = 1 if args.env_id == "RoboRugbySimple-v0" else R
+        acts = [torch.randint(0, 8, (K, n_local, A), generator=g, dtype=torch.uint8, device=dev) for _ in range(n_sets)]
+    else:  # GameEnv.step: one (left, right) thrust pair per robot, rounded to {-1, 0, 1} by the env (RR_Robot.py:100-102)
+        acts = [(torch.rand((K, n_local, 2 * R), generator=g, device=dev) * 2.9 - 1.45).float() for _ in range(n_sets)]
     acts_host = [a.cpu().pin_memory() for a in acts]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
@@ -234,7 +241,8 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = total * K * e2e_steps / float(t.item())
-    h2d = K * n_local * R
+    act_bytes = acts[0].element_size() * acts[0].shape[-1]  # per env-step
+    h2d = K * n_local * act_bytes
     d2h = K * n_local * (2 * D * 4 + 2 * 4 + 1)
     sampler.stop()
 
@@ -244,7 +252,7 @@ def main():
     if rank == 0:
         peak, peak_src = _peaks()
         S = env.state_bytes_per_env
-        q = 2.0 * S / K + R + 2 * D * 4 + 2 * 4 + 1  # algorithmic bytes per env-step
+        q = 2.0 * S / K + act_bytes + 2 * D * 4 + 2 * 4 + 1  # algorithmic bytes per env-step
         bytes_per_launch = q * n_local * K
         avg_kernel_s = (sum(kernel_ms) / len(kernel_ms)) * 1e-3
         achieved = bytes_per_launch / avg_kernel_s / 1e9
