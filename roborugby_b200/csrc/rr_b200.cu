@@ -58,7 +58,6 @@ static inline int pick_block(int64_t n, int sms, int max_block) {
   return (int)b;
 }
 
-extern __shared__ double rr_smem[];
 
 // Stage the sin/cos table in shared memory (all threads of the block; followed by a barrier).
 __device__ __forceinline__ const double *stage_trig_table() {
@@ -68,12 +67,14 @@ __device__ __forceinline__ const double *stage_trig_table() {
   return rr_smem;
 }
 __device__ __forceinline__ double *env_smem_base() { return rr_smem + kTrigRows * 4 + threadIdx.x; }
+__device__ __forceinline__ int env_smem_offset() { return kTrigRows * 4 + (int)threadIdx.x; }
 
 // HBM column -> (hot shared / cold local) fields.  Robot columns: cx,cy,l,r,t,b,rot,hx,hy,hrot.
 template <class L>
 __device__ __forceinline__ void load_env(typename L::E &e, double *cold, const Consts &k, const double *__restrict__ sf,
                                          const int32_t *__restrict__ si, int64_t N, int64_t i) {
   e.base = env_smem_base();
+  e.boff = env_smem_offset();
   e.cold = cold;
   e.stride = (int)blockDim.x;
   int f = 0;
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_step(const __grid_constant_
   if (live) {
     load_env<L>(e, cold, k, a.sf, a.si, a.N, i);
   } else {
-    e.base = env_smem_base(); e.cold = cold; e.stride = (int)blockDim.x;
+    e.base = env_smem_base(); e.boff = env_smem_offset(); e.cold = cold; e.stride = (int)blockDim.x;
     e.err = 0; e.step = 0; e.masks_dirty = false;
   }
   const int dim = obs_dim_of<E>(k.observer);
@@ -284,11 +285,13 @@ template <class L>
 __global__ void __launch_bounds__(L::kMaxBlock, 1) k_init(const __grid_constant__ Consts k, double *sf, int32_t *si, int64_t N,
                                                     double *start) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const double *trig_tab = stage_trig_table();  // every thread of the block takes part (barrier inside)
   if (i >= N) return;
   typename L::E e;
   double cold[L::E::kColdDoubles];
-  e.trig = &kSinCosDev[0][0];
+  e.trig = trig_tab;
   e.base = env_smem_base();
+  e.boff = env_smem_offset();
   e.cold = cold;
   e.stride = (int)blockDim.x;
   construct_env(e);
@@ -302,11 +305,12 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_reset_fixed(const __grid_co
                                                            int64_t N, const uint8_t *mask, const double *start,
                                                            int as_constructed) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const double *trig_tab = stage_trig_table();  // every thread of the block takes part (barrier inside)
   if (i >= N) return;
   if (mask && !mask[i]) return;
   typename L::E e;
   double cold[L::E::kColdDoubles];
-  e.trig = &kSinCosDev[0][0];
+  e.trig = trig_tab;
   load_env<L>(e, cold, k, sf, si, N, i);
   if (as_constructed) {  // GameEnv(lst_starting_config): sprites freshly constructed at the origin (:85-116)
     const unsigned ep = e.episode;
@@ -322,11 +326,12 @@ template <class L>
 __global__ void __launch_bounds__(L::kMaxBlock, 1) k_reset(const __grid_constant__ Consts k, double *sf, int32_t *si, int64_t N,
                                                      const uint8_t *mask) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const double *trig_tab = stage_trig_table();  // every thread of the block takes part (barrier inside)
   if (i >= N) return;
   if (mask && !mask[i]) return;
   typename L::E e;
   double cold[L::E::kColdDoubles];
-  e.trig = &kSinCosDev[0][0];
+  e.trig = trig_tab;
   load_env<L>(e, cold, k, sf, si, N, i);
   e.episode += 1;
   reset_env(e, k, (uint64_t)(k.env_offset + i));
@@ -337,10 +342,11 @@ template <class L, typename OutT>
 __global__ void __launch_bounds__(L::kMaxBlock, 1) k_observe(const __grid_constant__ Consts k, const double *sf, const int32_t *si,
                                                        int64_t N, void *obs_h, void *obs_g) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const double *trig_tab = stage_trig_table();  // every thread of the block takes part (barrier inside)
   if (i >= N) return;
   typename L::E e;
   double cold[L::E::kColdDoubles];
-  e.trig = &kSinCosDev[0][0];
+  e.trig = trig_tab;
   load_env<L>(e, cold, k, sf, si, N, i);
   const int dim = obs_dim_of<typename L::E>(k.observer);
   double ob[kMaxObs];

@@ -137,6 +137,10 @@ __device__ const double kSinCosDev[kTrigRows][4] = {RR_SINCOS_ROWS RR_SINCOS_GRI
 #undef RR_SINCOS_ROWS
 #undef RR_SINCOS_GRID_ROWS
 
+#ifdef __CUDACC__
+extern __shared__ double rr_smem[];  // the kernels' dynamic shared memory; the tables are staged at its start
+#endif
+
 RR_HD __forceinline__ double rr_fma(double a, double b, double c) { return fma(a, b, c); }
 
 struct SinCos { double s, c; };  // returned in registers (no pointer outputs: those force local-memory traffic)
@@ -147,6 +151,9 @@ struct SinCos { double s, c; };  // returned in registers (no pointer outputs: t
 // Valid for |x| < 16 (n <= 10 keeps n*p1 and n*p2 exact); the simulator's arguments lie in [-1.6, 7.9].
 // Every multiply-add below is an explicit fma, so the host build and the GPU round identically.
 RR_HD __noinline__ SinCos rr_sincos_dd(double x, const double *tab) {
+#ifdef __CUDA_ARCH__
+  tab = rr_smem;
+#endif
   SinCos out;
   if (!(fabs(x) < 16.0)) {  // not produced by the simulator; keep libm semantics for inf/nan/huge
     sincos(x, &out.s, &out.c);
@@ -225,6 +232,9 @@ RR_HD __noinline__ SinCos rr_sincos_dd(double x, const double *tab) {
 // Anything else (|x| >= 16, an angle off the grid) goes to rr_sincos_dd: same contract, same bits on host
 // and GPU.  profiles/README.md v11: rr_sincos_dd was 33 % of all executed instructions.
 RR_HD __noinline__ SinCos rr_sincos_grid(double x, const double *tab) {
+#ifdef __CUDA_ARCH__
+  tab = rr_smem;  // every kernel stages the table at the start of its shared memory (rr_b200.cu stage_trig_table): LDS
+#endif
   const double fn = rint(x * RR_GRID_INV_STEP);
   const double t = rr_fma(-fn, RR_GRID_C1, x);  // exact: fn * c1 fits 53 bits and is within a factor 2 of x
   const double q = fn * RR_GRID_C2;
