@@ -34,11 +34,11 @@ ENV_ID = "RoboRugbySimpleDuel-v2"
 ENVS_PER_GPU = 65536
 FUSED = 32
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_step launch (65 536 envs x 16 steps) from the committed
-# ncu captures (GAME: profiles/r01_v12b_k_step_game_traffic.csv, the committed kernel with streaming result stores;
-# TRAIN: profiles/r01_v12_k_step_train_by_function.txt, first two lines); reported as roofline.traffic when the
-# bench runs that exact workload.  (GAME: 152.6 MB read + 1302.5 MB written, mostly write-back of the per-thread
-# local arrays, which do not fit the L2 next to the state; algorithmic bytes are 226 MB.)
-NCU_TRAFFIC_BYTES = {"GAME": 1455.2e6, "TRAIN": 138.5e6}
+# `ncu --set full` captures of the committed kernel, profiles/r01_v13_k_step_{game,train}_by_function.txt (first two
+# lines); reported as roofline.traffic when the bench runs that exact workload.  (GAME: 172.0 MB read + 1392.5 MB
+# written, mostly write-back of the per-thread local arrays, which do not fit the L2 next to the state;
+# algorithmic bytes are 226 MB.)
+NCU_TRAFFIC_BYTES = {"GAME": 1564.5e6, "TRAIN": 117.5e6}
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 
@@ -266,7 +266,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (NCU_TRAFFIC_BYTES[args.preset] if (args.envs, args.fused) == (ENVS_PER_GPU, FUSED)
                                      else None),
-                         "traffic_source": ("profiles/r01_v12b_k_step_game_traffic.csv" if args.preset == "GAME" else "profiles/r01_v12_k_step_train_by_function.txt") + " (dram bytes read + written per launch)",
+                         "traffic_source": "profiles/r01_v13_k_step_%s_by_function.txt (dram bytes read + written per launch)" % args.preset.lower(),
                          "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src, "bytes_per_env_step": q, "state_bytes": S,
                          "kernel": "rr::k_step<2,2,4,4,float>" if args.preset == "GAME" else "rr::k_step<1,0,1,0,float>",
                          "note": "path is fp64-issue bound, not HBM bound (DESIGN.md §4)"},
