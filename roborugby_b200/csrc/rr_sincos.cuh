@@ -231,15 +231,16 @@ RR_HD __noinline__ SinCos rr_sincos_dd(double x, const double *tab) {
 // result is the correctly rounded one (d^3/6 < 2^-110 is dropped: the fast path requires |d| < 2^-36).
 // Anything else (|x| >= 16, an angle off the grid) goes to rr_sincos_dd: same contract, same bits on host
 // and GPU.  profiles/README.md v11: rr_sincos_dd was 33 % of all executed instructions.
-RR_HD __noinline__ SinCos rr_sincos_grid(double x, const double *tab) {
-#ifdef __CUDA_ARCH__
-  tab = rr_smem;  // every kernel stages the table at the start of its shared memory (rr_b200.cu stage_trig_table): LDS
-#endif
-  const double fn = rint(x * RR_GRID_INV_STEP);
-  const double t = rr_fma(-fn, RR_GRID_C1, x);  // exact: fn * c1 fits 53 bits and is within a factor 2 of x
+// The fast path as straight-line code: `ok` says whether x was a grid angle in range (otherwise the value is meaningless
+// but the computation is still safe: it runs on 0 instead of x).
+RR_HD __forceinline__ SinCos grid_core(double x, const double *tab, bool &ok) {
+  const bool in_range = fabs(x) < 16.0;
+  const double xs = in_range ? x : 0.0;
+  const double fn = rint(xs * RR_GRID_INV_STEP);
+  const double t = rr_fma(-fn, RR_GRID_C1, xs);  // exact: fn * c1 fits 53 bits and is within a factor 2 of x
   const double q = fn * RR_GRID_C2;
   const double dh = t - q;
-  if (!(fabs(x) < 16.0) || !(fabs(dh) < 0x1p-36)) return rr_sincos_dd(x, tab);
+  ok = in_range && fabs(dh) < 0x1p-36;
   const double bv = dh - t;  // TwoSum(t, -q)
   const double dl = ((t - (dh - bv)) + (-q - bv)) - rr_fma(fn, RR_GRID_C3, rr_fma(fn, RR_GRID_C2, -q));
   const int Np = (int)fn + 12 * kGridRows;  // |fn| <= 4584 for |x| < 16: positive dividend, quadrant unchanged
@@ -268,6 +269,32 @@ RR_HD __noinline__ SinCos rr_sincos_grid(double x, const double *tab) {
   SinCos out;
   out.s = (quad & 2) ? -so : so;
   out.c = (quad == 1 || quad == 2) ? -co : co;
+  return out;
+}
+
+RR_HD __noinline__ SinCos rr_sincos_grid(double x, const double *tab) {
+#ifdef __CUDA_ARCH__
+  tab = rr_smem;  // every kernel stages the table at the start of its shared memory (rr_b200.cu stage_trig_table): LDS
+#endif
+  bool ok;
+  const SinCos r = grid_core(x, tab, ok);
+  return ok ? r : rr_sincos_dd(x, tab);
+}
+
+// Two angles at once: the two chains are independent and interleave (a robot that turns needs the sin/cos of its new
+// heading twice, for its corner table and for the pivot: rr_sim.cuh robot_move).
+struct SinCos2 { double s0, c0, s1, c1; };
+RR_HD __noinline__ SinCos2 rr_sincos_grid2(double x0, double x1, const double *tab) {
+#ifdef __CUDA_ARCH__
+  tab = rr_smem;
+#endif
+  bool ok0, ok1;
+  SinCos r0 = grid_core(x0, tab, ok0);
+  SinCos r1 = grid_core(x1, tab, ok1);
+  if (!ok0) r0 = rr_sincos_dd(x0, tab);
+  if (!ok1) r1 = rr_sincos_dd(x1, tab);
+  SinCos2 out;
+  out.s0 = r0.s; out.c0 = r0.c; out.s1 = r1.s; out.c1 = r1.c;
   return out;
 }
 
