@@ -403,3 +403,55 @@ def test_gpu_allcoords_with_prior_across_reset_matches_oracle(oracle):
     finally:
         oracle.scratch_mode(0)
     env.close()
+
+
+def test_gpu_config1_simple_v0_4096_envs_per_step_parity(oracle):
+    """BASELINE.json configs[1]: RoboRugbySimple-v0, 4096 envs on one GPU, ONE step from injected states against the CPU
+    restatement of the reference's step() (itself pinned bit for bit to the reference on the golden files).  The states
+    are the contact-rich golden states of the GAME preset, tiled to 4096 with independent random actions; v0 drives
+    robot 0 only, the other robots keep the thrust stored in the state."""
+    V0 = "RoboRugbySimple-v0"
+    base = {k: [] for k in STATE_KEYS}
+    for f in FILES:
+        p, env_id, kind = parse_name(f)
+        if p != "GAME":
+            continue
+        d = np.load(f)
+        ok = d["exc"].sum(1) == 0
+        for k in STATE_KEYS:
+            x = d[k][ok][:, :-1]
+            base[k].append(x.reshape((-1,) + x.shape[2:]))
+    base = {k: np.concatenate(v) for k, v in base.items()}
+    N = 4096
+    idx = np.arange(N) % len(base["step"])
+    pool = {k: v[idx].copy() for k, v in base.items()}
+    pool["step"] = np.minimum(pool["step"], 100).astype(np.int32)
+    env = _venv(V0, N, "GAME")
+    env.set_state(pool)
+    g = torch.Generator().manual_seed(4096)
+    acts = torch.randint(0, 8, (1, N, 1), generator=g, dtype=torch.uint8)
+    obs_h, obs_g, rew, done = (x[0].cpu().numpy() for x in env.step_k(acts.cuda(), 1))
+    st, err, ng = env.get_state(), env.error_mask(), env.last_naughty()
+    oracle.scratch_mode(1)
+    try:
+        o = oracle.OracleEnv("GAME", V0)
+        bad, exact, worst, raised = [], 0, 0.0, 0
+        for i in range(N):
+            o.set_state({k: pool[k][i] for k in STATE_KEYS})
+            out = o.step(acts[0, i].numpy())
+            if out["err"]:
+                raised += 1
+                assert err[i] != 0, (i, "oracle raised, gpu did not")
+                continue
+            assert err[i] == 0, (i, "gpu raised, oracle did not", err[i])
+            got = dict(obs_h=obs_h[i], obs_g=obs_g[i], rew=rew[i], done=done[i], naughty=ng[i])
+            ok, ex, w, why = compare_record({k: st[k][i] for k in STATE_KEYS}, got, o.get_state(), out)
+            exact += ex
+            worst = max(worst, w)
+            if not ok:
+                bad.append((i, why, w))
+        print(f"configs[1]: {N} envs, {exact} bit-identical, {raised} raised on both sides, max abs err {worst:.3e}")
+        assert not bad, bad[:5]
+    finally:
+        oracle.scratch_mode(0)
+    env.close()
