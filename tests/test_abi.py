@@ -73,3 +73,21 @@ def test_reward_mixin_composition_to_config():
     import pytest
     with pytest.raises(ValueError):
         f(["NoSuchMixin"])
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """bench.py --impl reference (the CPU arm the driver runs next to ours) needs no GPU: one JSON line with the
+    contract's keys, timed on the C oracle port."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--preset", "TRAIN"], capture_output=True, text=True, timeout=300, check=True)
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["metric"] == "env_steps_per_sec" and d["unit"] == "env-steps/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["gpu_launches"] == 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["env_id"] == "RoboRugbySimpleDuel-v2" and d["config"]["preset"] == "TRAIN"
