@@ -35,10 +35,10 @@ ENVS_PER_GPU = 65536
 FUSED = 32
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE k_step launch (65 536 envs x 16 steps) from the committed
 # `ncu --set full` captures of the committed kernel, profiles/r01_v13_k_step_{game,train}_by_function.txt (first two
-# lines); reported as roofline.traffic when the bench runs that exact workload.  (GAME: 172.0 MB read + 1392.5 MB
+# lines); reported as roofline.traffic when the bench runs that exact workload.  (GAME: 163.6 MB read + 1349.8 MB
 # written, mostly write-back of the per-thread local arrays, which do not fit the L2 next to the state;
 # algorithmic bytes are 226 MB.)
-NCU_TRAFFIC_BYTES = {"GAME": 1564.5e6, "TRAIN": 117.5e6}
+NCU_TRAFFIC_BYTES = {"GAME": 1513.4e6, "TRAIN": 117.5e6}
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 
