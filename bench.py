@@ -125,7 +125,8 @@ def workload_config(args, world):
                         f"{'continuous thrust' if args.env_id == 'RoboRugby-v0' else 'discrete'} actions, "
                         f"{args.fused} fused env-steps per launch, auto-reset (BASELINE configs[{3 if args.env_id == 'RoboRugby-v0' else 2}])",
             "env_id": args.env_id, "preset": args.preset, "envs_per_gpu": args.envs, "fused_steps": args.fused,
-            "parallelism": f"env-shard x{world} (no data-path collective)", "l2": "flushed between timed launches"}
+            "parallelism": f"env-shard x{world} (no data-path collective)", "l2": "flushed between timed launches",
+            "strict_reset": not args.relaxed_reset, "squeeze_memo": not args.no_squeeze_memo, "out_dtype": "float32"}
 
 
 def main():
@@ -140,6 +141,9 @@ def main():
     ap.add_argument("--env-id", default=ENV_ID, help="another registered id, e.g. RoboRugby-v0 (the full game: continuous "
                     "thrust pairs for all robots, BASELINE configs[3]); the default is the workload the metric is quoted on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--relaxed-reset", action="store_true", help="strict_reset=0: two extra rejection rules in the reset "
+                    "placement (default: the reference's own placement)")
+    ap.add_argument("--no-squeeze-memo", action="store_true", help="A/B: recompute every pinned-ball frame (RR_FLAG_NO_SQUEEZE_MEMO)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -177,7 +181,8 @@ def main():
     total = N * world
     n_local, offset = shard_envs(total, rank, world)
     env = RoboRugbyVecEnv(args.env_id, n_local, preset=args.preset, device=dev, seed=2026, env_offset=offset,
-                          time_limit=True, auto_reset=True, out_dtype=torch.float32)
+                          time_limit=True, auto_reset=True, out_dtype=torch.float32, strict_reset=not args.relaxed_reset,
+                          flags=1 if args.no_squeeze_memo else 0)
     R, D = env.num_robots, env.obs_dim
     g = torch.Generator(device=dev).manual_seed(1 + rank)
     n_sets = 4  # rotate pre-generated action sets so consecutive launches differ

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define RR_ABI_VERSION 1
+#define RR_ABI_VERSION 2
 
 /* presets == the two constant sets behind RR_Constants.py:4 (GAME_MODE) */
 #define RR_PRESET_GAME 0  /* 800x800, 2+2 robots, 4+4 balls, 4500 steps */
@@ -91,7 +91,11 @@ extern "C" {
 #define RR_STAT_NAUGHTY 4
 #define RR_STAT_ERRORS 5
 #define RR_STAT_STEPS 6
+#define RR_STAT_REPLAYS 7 /* physics frames answered by the squeeze memo (rr_sim.cuh squeeze_contacts) */
 #define RR_NUM_STATS 8
+
+/* rr_config.flags */
+#define RR_FLAG_NO_SQUEEZE_MEMO 1u /* always recompute a pinned ball's failed frame (A/B switch; results are identical) */
 
 typedef struct rr_config {
   int32_t abi_version;  /* RR_ABI_VERSION */
@@ -108,6 +112,8 @@ typedef struct rr_config {
   uint32_t reward_order; /* RR_MIX_* sequence (see above); 0 = canonical order of the mixins in reward_mask */
   uint64_t seed;        /* Philox key */
   int64_t env_offset;   /* global index of this handle's env 0 (rank * n_envs when sharded) */
+  uint32_t flags;       /* RR_FLAG_* */
+  int32_t goal_scoring; /* reserved (0) */
 } rr_config;
 
 typedef struct rr_sim rr_sim;

@@ -105,6 +105,10 @@ int rro_reset_draws(rro_env *e, int randomize, const int32_t *draws, int n_draws
 /* Same reset, drawing from the counter-based generator the CUDA product uses (Philox4x32-10,
  * key = seed, counter = (env_index, episode, draw/4)); see include/rr_b200.h. */
 void rro_reset_philox(rro_env *e, uint64_t seed, uint64_t env_index, uint32_t episode);
+/* relaxed = 1: the product's strict_reset = 0 mode, which adds two rejection rules to the placement loop (a robot whose
+ * rotated rect intersects an already placed one; a ball within 14 px of another) so that no episode starts in a state
+ * on which the reference raises or hangs.  relaxed = 0 is the reference's placement. */
+void rro_reset_philox_mode(rro_env *e, uint64_t seed, uint64_t env_index, uint32_t episode, int relaxed);
 
 /* The reference keeps one module-global scratch rect whose centre is updated incrementally
  * (RR_TrashyPhysics.py:29-35,54-55).  mode 0 = faithful (state carried between calls, what the
@@ -115,6 +119,10 @@ void rro_scratch_reset(void);
 
 void rro_set_starting_positions(rro_env *e, const double *rob3, const double *ball2);
 long rro_rollout(rro_env *e, long n_steps, uint64_t seed);
+
+/* Test instrumentation: number of physics frames since the last clear in which all ten resolve passes failed and the
+ * undo loop ran (RR_EnvBase.py:284-287): the "ball pinned between a robot and a wall" frames. */
+long rro_debug_failed_frames(int clear);
 
 /* Philox4x32-10 exposed for the RNG known-answer test. */
 void rro_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);

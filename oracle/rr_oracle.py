@@ -66,9 +66,12 @@ def lib():
         L.rro_reset_draws.argtypes = [C.c_void_p, C.c_int, ip, C.c_int]
         L.rro_reset_draws.restype = C.c_int
         L.rro_reset_philox.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32]
+        L.rro_reset_philox_mode.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32, C.c_int]
         L.rro_set_starting_positions.argtypes = [C.c_void_p, dp, dp]
         L.rro_rollout.argtypes = [C.c_void_p, C.c_long, C.c_uint64]
         L.rro_rollout.restype = C.c_long
+        L.rro_debug_failed_frames.argtypes = [C.c_int]
+        L.rro_debug_failed_frames.restype = C.c_long
         L.rro_scratch_mode.argtypes = [C.c_int]
         L.rro_scratch_reset.argtypes = []
         L.rro_philox4x32.argtypes = [C.POINTER(C.c_uint32)] * 3
@@ -139,8 +142,9 @@ class OracleEnv:
         d = np.ascontiguousarray(draws, np.int32)
         return lib().rro_reset_draws(self._h, int(randomize), _ip(d), d.size)
 
-    def reset_philox(self, seed, env_index, episode):
-        lib().rro_reset_philox(self._h, int(seed), int(env_index), int(episode))
+    def reset_philox(self, seed, env_index, episode, relaxed=False):
+        """Placement from the product's counter-based stream; relaxed=True adds the strict_reset=0 rejection rules."""
+        lib().rro_reset_philox_mode(self._h, int(seed), int(env_index), int(episode), int(bool(relaxed)))
 
     def rollout(self, n_steps, seed):
         """n_steps random-action env-steps entirely in C (timing leg of bench.py)."""
@@ -153,6 +157,11 @@ class OracleEnv:
 
 def scratch_mode(fresh):
     lib().rro_scratch_mode(int(fresh))
+
+
+def failed_frames(clear=False):
+    """Pinned-ball frames (ten failed resolve passes + undo) executed since the last clear."""
+    return int(lib().rro_debug_failed_frames(int(clear)))
 
 
 def scratch_reset():

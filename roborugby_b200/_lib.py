@@ -9,12 +9,13 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RR_B200_LIB", os.path.join(_HERE, "librr_b200.so"))
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 PRESET_GAME, PRESET_TRAIN = 0, 1
 REW_CHASE, REW_PUSHPOS, REW_NAUGHTY = 1, 2, 4
 OBS_NONE, OBS_BASIC_LIDAR, OBS_LIDAR6_V2, OBS_ALLCOORDS = 0, 1, 2, 3
 NUM_STATS = 8
-STAT_NAMES = ("episodes", "return_happy", "return_grumpy", "length", "naughty", "errors", "steps", "reserved")
+STAT_NAMES = ("episodes", "return_happy", "return_grumpy", "length", "naughty", "errors", "steps", "squeeze_replays")
+FLAG_NO_SQUEEZE_MEMO = 1
 
 ERR_BITS = {
     1: "Game is over. Go home.",                                   # RR_EnvBase.py:262
@@ -36,6 +37,7 @@ class Config(C.Structure):
         ("observer", C.c_int32), ("discrete", C.c_int32), ("time_limit", C.c_int32),
         ("auto_reset", C.c_int32), ("out_f64", C.c_int32), ("strict_reset", C.c_int32),
         ("reward_order", C.c_uint32), ("seed", C.c_uint64), ("env_offset", C.c_int64),
+        ("flags", C.c_uint32), ("goal_scoring", C.c_int32),
     ]
 
 

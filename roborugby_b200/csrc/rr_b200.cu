@@ -77,6 +77,7 @@ __device__ __forceinline__ void load_env(typename L::E &e, double *cold, const C
   e.boff = env_smem_offset();
   e.cold = cold;
   e.stride = (int)blockDim.x;
+  e.memo_clear();
   int f = 0;
   e.hvalid = 0;
   e.thrust = 0;
@@ -272,7 +273,10 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_step(const __grid_constant_
 #ifdef RR_DEBUG_COUNT
   last_naughty = (int)((min(e.dbg[0], 32767u) << 16) | min(e.dbg[2], 65535u));  // slow passes | precise ball-robot tests
 #endif
-  if (live) store_env<L>(e, k, a.sf, a.si, a.N, i, last_naughty);
+  if (live) {
+    st[RR_STAT_REPLAYS] = e.mm(31);
+    store_env<L>(e, k, a.sf, a.si, a.N, i, last_naughty);
+  }
   // episode statistics: warp-shuffle reduction, one atomic per warp and statistic
 #pragma unroll
   for (int q = 0; q < RR_NUM_STATS; q++) {
@@ -423,6 +427,7 @@ int rr_default_config(rr_config *c, int preset, const char *env_id) {
   }
   c->auto_reset = 1;
   c->time_limit = 1;
+  c->strict_reset = 1;  // the reference's own placement rules
   return RR_OK;
 }
 

@@ -24,8 +24,8 @@ from .constants import ENV_IDS, get_preset
 
 class RoboRugbyVecEnv:
     def __init__(self, env_id="RoboRugbySimpleDuel-v2", num_envs=4096, preset="GAME", device="cuda:0", seed=0,
-                 env_offset=0, time_limit=True, auto_reset=True, out_dtype=torch.float32, strict_reset=False,
-                 n_actions=None, observer=None, reward_mask=None, reward_order=None, reward_mixins=None):
+                 env_offset=0, time_limit=True, auto_reset=True, out_dtype=torch.float32, strict_reset=True,
+                 n_actions=None, observer=None, reward_mask=None, reward_order=None, reward_mixins=None, flags=0):
         if env_id not in ENV_IDS:
             raise ValueError(f"unknown env id {env_id!r}; expected one of {ENV_IDS}")
         if not torch.cuda.is_available():
@@ -53,6 +53,7 @@ class RoboRugbyVecEnv:
             cfg.reward_order = 0
         if reward_order is not None:
             cfg.reward_order = int(reward_order)
+        cfg.flags = int(flags)
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         cfg.env_offset = int(env_offset)
         self.cfg = cfg

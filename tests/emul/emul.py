@@ -50,6 +50,8 @@ def lib():
         L.emul_sincos2.restype = None
         L.emul_predicates.argtypes = [C.POINTER(Config), vp, vp, vp, vp, vp, vp, vp]
         L.emul_predicates.restype = None
+        L.emul_last_replays.argtypes = []
+        L.emul_last_replays.restype = C.c_double
         _lib = L
     return _lib
 

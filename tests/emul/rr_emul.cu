@@ -41,6 +41,7 @@ static void load(E &e, const Consts &k, const double *rob, const double *rhist, 
   }
   e.step = step; e.err = 0; e.episode = 0; e.ret_h = e.ret_g = 0;
   e.invalidate_caches();
+  e.memo_clear();
 }
 
 template <class E>
@@ -59,6 +60,8 @@ static void store(const E &e, double *rob, double *rhist, int32_t *rflag, double
   }
   *step = e.step;
 }
+
+static double g_last_replays = 0.0;  // frames of the last emul_step answered by the squeeze memo
 
 template <int NH, int NG, int NP, int NN>
 static unsigned step_t(const Consts &k, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,
@@ -84,6 +87,7 @@ static unsigned step_t(const Consts &k, double *rob, double *rhist, int32_t *rfl
   }
   StepOut o;
   sim_step(e, k, cmd, n_cmd, o, true);
+  g_last_replays = e.mm(31);
   unsigned oerr = 0;
   if (obs_h) observe(e, k, 1, obs_h, oerr);
   if (obs_g) observe(e, k, -1, obs_g, oerr);
@@ -109,6 +113,8 @@ static unsigned reset_t(const Consts &k, double *rob, double *rhist, int32_t *rf
 }
 
 extern "C" {
+
+double emul_last_replays(void) { return g_last_replays; }
 
 unsigned emul_step(const rr_config *cfg, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,
                    const double *actions, int n_actions, double *obs_h, double *obs_g, double *rew, int32_t *done,

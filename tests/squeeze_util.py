@@ -1,0 +1,42 @@
+"""Hand-built "ball pinned between a robot and a wall" states (RR_EnvBase.py:345-454: ten failed resolve passes, then
+the undo loop, frame after frame): the configuration that the kernels' squeeze memo (rr_sim.cuh squeeze_contacts)
+replays instead of recomputing.  Used by the CPU and GPU tiers."""
+import numpy as np
+
+V2 = "RoboRugbySimpleDuel-v2"
+
+
+def scenario(rng, preset):
+    """(ball x, ball y, robot x, robot y, robot heading): robot 0 driving ball 0 into one of the four walls."""
+    W = 800 if preset == "GAME" else 600
+    y0 = rng.uniform(150, W - 150)
+    side = int(rng.integers(0, 4))
+    th, off, gap = rng.uniform(-12, 12), rng.uniform(-12, 12), rng.uniform(0.0, 3.0)
+    if side == 0:
+        sc = (7.3 + gap * 0.2, y0, 7.3 + 17 + gap, y0 + off, 180 + th)
+    elif side == 1:
+        sc = (W - 7.3 - gap * 0.2, y0, W - 7.3 - 17 - gap, y0 + off, 0 + th)
+    elif side == 2:
+        sc = (y0, 7.3 + gap * 0.2, y0 + off, 7.3 + 17 + gap, 90 + th)
+    else:
+        sc = (y0, W - 7.3 - gap * 0.2, y0 + off, W - 7.3 - 17 - gap, 270 + th)
+    return sc[:4] + (sc[4] % 360,)
+
+
+def oracle_env(oracle, preset, sc, time_limit=False):
+    """An oracle env reset (through the reference's own fixed-layout reset) to the scenario; the other robots and balls
+    sit in the middle of the arena, far from the squeeze."""
+    bx, by, rx, ry, rot = sc
+    o = oracle.OracleEnv(preset, V2, time_limit=time_limit)
+    W = 800 if preset == "GAME" else 600
+    rob3 = [(rx, ry, rot)] + [(W / 2 + 60 * (i - 1), W / 2 + 90 * (i - 2), 45.0 * i) for i in range(1, o.R)]
+    ball2 = [(bx, by)] + [(W / 2 - 150 + 40 * i, W / 2 + 200 - 30 * i) for i in range(1, o.B)]
+    o.set_starting_positions(np.array(rob3, float), np.array(ball2, float))
+    o.reset_draws([], randomize=False)
+    return o
+
+
+def actions(rng, n_robots, n_steps=6):
+    """Robot 0 keeps pushing forward (with one random action in between); the others move at random."""
+    lead = [0, 0, 0, int(rng.integers(0, 8)), 0, 0][:n_steps]
+    return np.array([[a0] + [int(x) for x in rng.integers(0, 8, n_robots - 1)] for a0 in lead], np.uint8)
