@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_step(const __grid_constant_
   last_naughty = (int)((min(e.dbg[0], 32767u) << 16) | min(e.dbg[2], 65535u));  // slow passes | precise ball-robot tests
 #endif
   if (live) {
-    st[RR_STAT_REPLAYS] = e.mm(31);
+    st[RR_STAT_REPLAYS] = e.mm(kMReplays);
     store_env<L>(e, k, a.sf, a.si, a.N, i, last_naughty);
   }
   // episode statistics: warp-shuffle reduction, one atomic per warp and statistic

@@ -87,7 +87,7 @@ static unsigned step_t(const Consts &k, double *rob, double *rhist, int32_t *rfl
   }
   StepOut o;
   sim_step(e, k, cmd, n_cmd, o, true);
-  g_last_replays = e.mm(31);
+  g_last_replays = e.mm(kMReplays);
   unsigned oerr = 0;
   if (obs_h) observe(e, k, 1, obs_h, oerr);
   if (obs_g) observe(e, k, -1, obs_g, oerr);

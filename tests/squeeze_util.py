@@ -23,14 +23,38 @@ def scenario(rng, preset):
     return sc[:4] + (sc[4] % 360,)
 
 
-def oracle_env(oracle, preset, sc, time_limit=False):
+def oracle_env(oracle, preset, sc, time_limit=False, spectators=None):
     """An oracle env reset (through the reference's own fixed-layout reset) to the scenario; the other robots and balls
-    sit in the middle of the arena, far from the squeeze."""
+    sit in the middle of the arena, far from the squeeze, except `spectators` = (dx, dy) offsets from the pinned ball
+    at which ball 1 (and robot 1, if a second offset is given) are placed: bystanders at a wall next to the squeeze."""
     bx, by, rx, ry, rot = sc
     o = oracle.OracleEnv(preset, V2, time_limit=time_limit)
     W = 800 if preset == "GAME" else 600
     rob3 = [(rx, ry, rot)] + [(W / 2 + 60 * (i - 1), W / 2 + 90 * (i - 2), 45.0 * i) for i in range(1, o.R)]
     ball2 = [(bx, by)] + [(W / 2 - 150 + 40 * i, W / 2 + 200 - 30 * i) for i in range(1, o.B)]
+    if spectators and o.B > 1:
+        clip = lambda v: float(min(max(v, 8.0), W - 8.0))
+        ball2[1] = (clip(bx + spectators[0][0]), clip(by + spectators[0][1]))
+        if len(spectators) > 1 and o.R > 1:
+            rob3[1] = (float(min(max(bx + spectators[1][0], 60.0), W - 60.0)), float(min(max(by + spectators[1][1], 60.0), W - 60.0)), 30.0)
+    o.set_starting_positions(np.array(rob3, float), np.array(ball2, float))
+    o.reset_draws([], randomize=False)
+    return o
+
+
+def pincer_env(oracle, rng, time_limit=False):
+    """GAME preset: ball 0 in the open between robots 0 and 1, which drive at each other (a squeeze without a wall)."""
+    o = oracle.OracleEnv("GAME", V2, time_limit=time_limit)
+    W = 800
+    x0, y0 = rng.uniform(200, 600), rng.uniform(200, 600)
+    ang = rng.uniform(0, 360)
+    ca, sa = np.cos(np.radians(ang)), -np.sin(np.radians(ang))      # heading `ang` drives along (cos, -sin)
+    g0, g1 = rng.uniform(17.5, 20), rng.uniform(17.5, 20)
+    j0, j1 = rng.uniform(-8, 8), rng.uniform(-8, 8)                 # sideways offsets, degrees of misalignment
+    rob3 = [(x0 - g0 * ca - j0 * sa, y0 - g0 * sa + j0 * ca, (ang + rng.uniform(-6, 6)) % 360),
+            (x0 + g1 * ca - j1 * sa, y0 + g1 * sa + j1 * ca, (ang + 180 + rng.uniform(-6, 6)) % 360)]
+    rob3 += [(100.0 + 600 * (x0 < 400), 100.0, 45.0), (100.0 + 600 * (x0 < 400), 700.0, 135.0)]
+    ball2 = [(x0, y0)] + [(60.0 + 90 * i, 40.0 + 720 * (y0 < 400)) for i in range(1, o.B)]
     o.set_starting_positions(np.array(rob3, float), np.array(ball2, float))
     o.reset_draws([], randomize=False)
     return o

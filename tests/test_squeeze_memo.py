@@ -7,7 +7,7 @@ Also pins the relaxed reset placement (strict_reset = 0) of the kernels against 
 import numpy as np
 import pytest
 
-from squeeze_util import V2, actions, oracle_env, scenario
+from squeeze_util import V2, actions, oracle_env, pincer_env, scenario
 
 
 def _cfg(preset, flags):
@@ -19,7 +19,7 @@ def _cfg(preset, flags):
     return cfg
 
 
-@pytest.mark.parametrize("seed", [0, 1])
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
 def test_squeeze_memo_replay_is_exact(oracle, seed):
     from emul import emul
     from emul.emul import EmulEnv
@@ -31,13 +31,27 @@ def test_squeeze_memo_replay_is_exact(oracle, seed):
     try:
         for it in range(60):
             preset = "GAME" if it % 4 else "TRAIN"
-            o = oracle_env(oracle, preset, scenario(rng, preset))
+            spect = None
+            if seed == 2:   # bystanders next to the squeeze: a ball 16-45 px away, sometimes a robot 35-80 px away
+                ang, d = rng.uniform(0, 2 * np.pi), rng.uniform(16, 45)
+                spect = [(d * np.cos(ang), d * np.sin(ang))]
+                if it % 3 == 0:
+                    ang, d = rng.uniform(0, 2 * np.pi), rng.uniform(35, 80)
+                    spect.append((d * np.cos(ang), d * np.sin(ang)))
+            if seed == 3:   # a ball pinned between two robots driving at each other
+                preset = "GAME"
+                o = pincer_env(oracle, rng)
+            else:
+                o = oracle_env(oracle, preset, scenario(rng, preset), spectators=spect)
             st0 = o.get_state()
             on = EmulEnv(_cfg(preset, 0), o.R, o.B, 5)
             off = EmulEnv(_cfg(preset, _lib.FLAG_NO_SQUEEZE_MEMO), o.R, o.B, 5)
             on.set_state(st0); off.set_state(st0)
             oracle.failed_frames(True)
-            for a in actions(rng, o.R):
+            acts = actions(rng, o.R)
+            if seed == 3:
+                acts[:, 1] = acts[:, 0]   # robot 1 pushes too
+            for a in acts:
                 r_on = on.step(a)
                 replays += emul.lib().emul_last_replays()
                 r_off = off.step(a)
@@ -46,6 +60,8 @@ def test_squeeze_memo_replay_is_exact(oracle, seed):
                 for k in s_on:   # memo on == memo off, bit for bit
                     assert np.array_equal(s_on[k], s_off[k]), (it, k)
                 assert r_on["err"] == r_off["err"] == r_o["err"]
+                if r_on["err"]:   # the reference raised (e.g. a bystander robot placed on top of the pushing one)
+                    break
                 for k in ("rew", "obs_h", "obs_g"):
                     assert np.array_equal(r_on[k], r_off[k], equal_nan=True), (it, k)
                 assert r_on["naughty"] == r_off["naughty"] == r_o["naughty"]
@@ -54,14 +70,12 @@ def test_squeeze_memo_replay_is_exact(oracle, seed):
                 for k in ("rob", "rhist", "ball"):   # ... and both == the oracle
                     assert np.allclose(s_on[k], s_o[k], rtol=1e-9, atol=1e-9), (it, k)
                 assert np.allclose(r_on["rew"], r_o["rew"], rtol=1e-9, atol=1e-9)
-                if r_on["err"]:
-                    break
             failed += oracle.failed_frames(True)
     finally:
         emul.use_libm_sincos(False)
         oracle.scratch_mode(0)
     print(f"seed {seed}: {failed} pinned-ball frames in the oracle, {int(replays)} replayed by the memo")
-    assert failed > 1500 and replays > 0.7 * failed
+    assert failed > (1500 if seed < 3 else 200) and replays > (0.7 if seed < 2 else 0.4) * failed
 
 
 @pytest.mark.parametrize("preset", ["GAME", "TRAIN"])
