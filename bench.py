@@ -12,8 +12,11 @@ with in-kernel auto-reset.  One bench "step" = one fused launch = 65 536 x 32 en
            max over ranks, L2 flushed between timed launches
   e2e      the same launches through the HOST-buffer C-ABI entry point rr_step_host: actions copied
            host->device and observations/rewards/done copied device->host inside the timed region
-  roofline HBM: algorithmic bytes per launch / measured kernel time vs MEASURED_PEAKS.json
+  roofline HBM: algorithmic bytes per launch / measured kernel time vs MEASURED_PEAKS.json; `secondary` carries the
+           ncu figures that actually bound the kernel (fp64 pipe, issue slots, SM busy) and the file they come from
   cpu_baseline  the C oracle (port of the reference algorithm, oracle/) on the host cores, N=1 only
+  extras   k1: the same batch stepped ONE env-step per launch (env.step(), the call a policy-in-the-loop consumer
+           makes); dqn: env-steps/s inside the vectorised DQN loop (BASELINE configs[4]); per_rank_kernel_ms (N > 1)
 
 --impl reference times the reference algorithm's CPU implementation on the host cores (the C
 oracle port; the Python reference itself cannot travel to the GPU box — its measured rate in the
@@ -33,12 +36,22 @@ sys.path.insert(0, ROOT)
 ENV_ID = "RoboRugbySimpleDuel-v2"
 ENVS_PER_GPU = 65536
 FUSED = 32
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_step launch (65 536 envs x 16 steps) from the committed
-# `ncu --set full` captures of the committed kernel, profiles/r01_v13_k_step_{game,train}_by_function.txt (first two
-# lines); reported as roofline.traffic when the bench runs that exact workload.  (GAME: 163.6 MB read + 1349.8 MB
-# written, mostly write-back of the per-thread local arrays, which do not fit the L2 next to the state;
-# algorithmic bytes are 226 MB.)
+# Figures of ONE k_step launch of the bench workload (65 536 envs x 32 steps) from the committed `ncu --set full`
+# capture of the committed kernel (profiles/, see PROFILE_SOURCE): dram__bytes_read.sum + dram__bytes_write.sum
+# (reported as roofline.traffic when the bench runs that exact workload) and the pipe / issue / SM-busy figures that
+# bound the kernel (reported as roofline.secondary; the path is not HBM-bound).
+PROFILE_SOURCE = {"GAME": "profiles/r01_v13_k_step_game_by_function.txt", "TRAIN": "profiles/r01_v13_k_step_train_by_function.txt"}
 NCU_TRAFFIC_BYTES = {"GAME": 1513.4e6, "TRAIN": 117.5e6}
+NCU_SECONDARY = {
+    "GAME": {"fp64_pipe_pct": 17.0, "issue_slots_busy_pct": 27.6, "warps_active_pct": 21.8, "sm_busy_frac": 0.43,
+             "barrier_stall_per_issue": 3.87, "long_scoreboard_per_issue": 2.04},
+    "TRAIN": {"fp64_pipe_pct": 25.3, "issue_slots_busy_pct": 38.3},
+}
+KERNEL_NAME = {"GAME": "rr::k_step<rr::Launch<2,2,4,4>,float>", "TRAIN": "rr::k_step<rr::Launch<1,0,1,0>,float>"}
+# The Python reference itself (unmodified, stub pygame/gym) cannot travel to the GPU box; its own rate, measured in the
+# build container with oracle/time_reference.py (8 cores, one process per core), is recorded beside the port's.
+PY_REFERENCE_NOTE = {"GAME": "Python reference (oracle/time_reference.py, build container, 8 cores): 123 env-steps/s (18.9 per core)",
+                     "TRAIN": "Python reference (oracle/time_reference.py, build container, 8 cores): 4467 env-steps/s (657 per core)"}
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 
@@ -114,10 +127,42 @@ def run_reference(args, rank, world):
         "warmup": args.warmup, "ms_per_step": 1e3 * sum(walls) / len(walls), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args, world),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "note": PY_REFERENCE_NOTE[args.preset]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }), flush=True)
+
+
+def dqn_rate(dev, envs, steps, preset="TRAIN"):
+    """env-steps/s inside the vectorised Training_DQN_pytorch loop (roborugby_b200/dqn.py): eps-greedy acting, env step,
+    replay store and one learn() per step, all on the device."""
+    import torch
+    from roborugby_b200.dqn import VecDQNAgent, train
+    from roborugby_b200.vec_env import RoboRugbyVecEnv
+    env = RoboRugbyVecEnv(ENV_ID, envs, preset=preset, device=dev, seed=5, n_actions=1)
+    agent = VecDQNAgent(env.obs_dim, batch_size=2500, max_mem_size=500000, device=dev, seed=1)
+    train(env, agent, 10)  # warm-up (cuBLAS handles, allocator)
+    out = train(env, agent, steps)
+    env.close()
+    return {"value": out["env_steps_per_s"], "unit": UNIT, "envs": envs, "steps": steps, "preset": preset,
+            "transitions_stored": out["transitions"], "learn_every": 1, "batch_size": 2500,
+            "note": "Training_DQN_pytorch.py:317-377 on the GPU VecEnv, K = 1 launches, nothing visits the host"}
+
+
+def run_dqn(args, rank, world, local_rank):
+    """--workload dqn: BASELINE configs[4] as its own line (rank 0 only; the loop does not shard)."""
+    if rank != 0:
+        return
+    import torch
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    r = dqn_rate(dev, envs=args.envs, steps=max(args.steps, 30))
+    print(json.dumps({"metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": 1, "steps": r["steps"], "warmup": 10,
+                      "ms_per_step": 1e3 * r["envs"] / r["value"], "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                      "config": {"workload": f"Training_DQN_pytorch loop on {ENV_ID}, TRAIN preset, {r['envs']} envs, learn() every "
+                                             "step, batch 2500 (BASELINE configs[4])"}, "dqn": r}), flush=True)
 
 
 def workload_config(args, world):
@@ -144,6 +189,9 @@ def main():
     ap.add_argument("--relaxed-reset", action="store_true", help="strict_reset=0: two extra rejection rules in the reset "
                     "placement (default: the reference's own placement)")
     ap.add_argument("--no-squeeze-memo", action="store_true", help="A/B: recompute every pinned-ball frame (RR_FLAG_NO_SQUEEZE_MEMO)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the K = 1 and DQN-loop extras")
+    ap.add_argument("--workload", default="rollout", choices=["rollout", "dqn"], help="dqn: BASELINE configs[4], the "
+                    "Training_DQN_pytorch loop on the GPU VecEnv (TRAIN constants, as the reference script requires)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -152,6 +200,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         run_reference(args, rank, world)
+        return
+    if args.workload == "dqn":
+        run_dqn(args, rank, world, local_rank)
         return
 
     # CPU baseline first (rank 0, N=1 only), before this process touches CUDA
@@ -163,7 +214,8 @@ def main():
         v, wall = rr_oracle.timed_rollout(args.preset, args.env_id, per_core, cores)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"{per_core} random-action env-steps per core on {cores} cores ({wall:.1f} s), "
-                                  f"C oracle port of the reference algorithm, same env id and preset"}
+                                  f"C oracle port of the reference algorithm, same env id and preset",
+                        "note": PY_REFERENCE_NOTE[args.preset]}
 
     import torch
     import torch.distributed as dist
@@ -231,6 +283,11 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     max_ms = float(t.item())
     value = total * K * args.steps / (max_ms * 1e-3)
+    per_rank_ms = [my_ms / args.steps]
+    if world > 1:  # per-rank mean launch time: the max over ranks is the shard with the slowest envs (no collective inside)
+        allms = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(allms, torch.tensor([my_ms / args.steps], dtype=torch.float64, device=dev))
+        per_rank_ms = [float(x.item()) for x in allms]
 
     # ---------------- end-to-end through the host-buffer C-ABI entry point ----------------
     e2e_steps = max(3, min(args.steps, 10))
@@ -253,6 +310,31 @@ def main():
 
     stats = env.reduce_stats()  # the one optional collective: 64-byte all-reduce of episode statistics
     err_envs = int((env.error_mask() != 0).sum())
+    local_stats = env.get_stats()
+
+    # ---------------- extras: one env-step per launch (env.step()), DQN loop ----------------
+    extras = {"per_rank_kernel_ms": per_rank_ms}
+    if not args.no_extras:
+        n1 = 256
+        a1 = [a[j:j + 1] for a in acts for j in range(K)]  # the same action stream as above, one row per launch
+        for w in range(5):
+            env.step_k(a1[w % len(a1)], 1)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for s in range(n1):
+            env.step_k(a1[(5 + s) % len(a1)], 1)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        extras["k1"] = {"value": total * n1 / (float(t.item()) * 1e-3), "unit": UNIT, "launches": n1,
+                        "ms_per_launch": float(t.item()) / n1,
+                        "note": "one env-step per launch (RoboRugbyVecEnv.step / GameEnv.step, RR_EnvBase.py:260), "
+                                "actions resident, back-to-back launches, no L2 flush"}
+        if rank == 0 and world == 1:
+            extras["dqn"] = dqn_rate(dev, envs=4096, steps=120)
 
     if rank == 0:
         peak, peak_src = _peaks()
@@ -271,15 +353,19 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (NCU_TRAFFIC_BYTES[args.preset] if (args.envs, args.fused) == (ENVS_PER_GPU, FUSED)
                                      else None),
-                         "traffic_source": "profiles/r01_v13_k_step_%s_by_function.txt (dram bytes read + written per launch)" % args.preset.lower(),
+                         "traffic_source": PROFILE_SOURCE[args.preset] + " (dram bytes read + written per launch)",
                          "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src, "bytes_per_env_step": q, "state_bytes": S,
-                         "kernel": "rr::k_step<2,2,4,4,float>" if args.preset == "GAME" else "rr::k_step<1,0,1,0,float>",
-                         "note": "path is fp64-issue bound, not HBM bound (DESIGN.md §4)"},
+                         "kernel": KERNEL_NAME[args.preset],
+                         "secondary": dict(NCU_SECONDARY[args.preset], source=PROFILE_SOURCE[args.preset]),
+                         "note": "path is fp64-issue / latency bound, not HBM bound (DESIGN.md §4)"},
             "clocks": sampler.summary(),
             "episode_stats": {k: stats[k] for k in ("episodes", "mean_return_happy", "mean_return_grumpy", "mean_length",
                                                     "naughty", "errors", "steps")},
             "error_envs": err_envs,
+            "errors_per_million_env_steps": 1e6 * stats["errors"] / max(stats["steps"], 1.0),
+            "squeeze_replays_rank0": local_stats.get("squeeze_replays"),
             "wall_s_timed_region": t_wall,
+            "extras": extras,
         }
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline

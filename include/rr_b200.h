@@ -76,6 +76,7 @@ extern "C" {
 #define RR_ERR_COINCIDENT_BALLS 64u /* RR_TrashyPhysics.py:249-250 */
 #define RR_ERR_DIV0 128u            /* MyUtils.py:25         */
 #define RR_ERR_RESET_PLACEMENT 256u /* placement loop exceeded its bound (reference: unbounded) */
+#define RR_ERR_BAD_ACTION 512u      /* discrete action id > 7: KeyError in thrust_from_direction before anything moves, RR_EnvBase.py:593-606, :624 */
 
 /* return codes */
 #define RR_OK 0

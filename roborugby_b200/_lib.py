@@ -27,6 +27,7 @@ ERR_BITS = {
     64: "Really tho?? The balls are in the EXACT same spot????",  # RR_TrashyPhysics.py:250
     128: "Numerator AND Denominator are both 0.",                 # MyUtils.py:25
     256: "reset placement loop exceeded its bound",
+    512: "KeyError: discrete action id outside 0..7",              # RR_EnvBase.py:593-606 (dict lookup)
 }
 
 

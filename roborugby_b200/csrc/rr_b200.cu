@@ -16,6 +16,7 @@
 // episode statistics at the end of the launch.
 #include <cmath>
 #include <cstdio>
+#include <cstdint>
 #include <cstring>
 #include <new>
 #include <string>
@@ -37,8 +38,11 @@ struct Launch {
   // largest block: bounded by 227 KB of shared memory and by 65 536 registers per SM
   static constexpr int kMaxBlock = R > 1 ? 448 : 512;
   static constexpr int kTrigDoubles = kTrigRows * 4;  // sin/cos tables staged in front of the env fields
+  // behind the env fields: one 640-byte staging area per warp, through which a warp's result rows (160 floats of
+  // observations, 64 of rewards, 32 done bytes) are turned into full 128-bit stores (warp_store_rows)
+  static constexpr int kStageBytes = 640;
   static constexpr size_t smem_bytes(int block) {
-    return sizeof(double) * (kTrigDoubles + E::kDoubles * (size_t)block);
+    return sizeof(double) * (kTrigDoubles + E::kDoubles * (size_t)block) + (size_t)kStageBytes * (block / 32);
   }
   // HBM structure-of-arrays layout
   static constexpr int kRobotF = 10, kBallF = 8;
@@ -78,6 +82,7 @@ __device__ __forceinline__ void load_env(typename L::E &e, double *cold, const C
   e.cold = cold;
   e.stride = (int)blockDim.x;
   e.memo_clear();
+  e.sq_watch = 0;
   int f = 0;
   e.hvalid = 0;
   e.thrust = 0;
@@ -152,6 +157,38 @@ __device__ __forceinline__ void store_env(const typename L::E &e, const Consts &
   si[(L::R + 3) * N + i] = last_naughty;
 }
 
+// Result rows of one warp: lane l holds `dim` values that belong at dst[l * dim .. l * dim + dim), so the warp's 32 rows
+// are one contiguous range.  The values are converted, staged in the warp's shared-memory area and written as full
+// 128-bit streaming stores (STG.E.128, evict-first: results are never read back by the kernel); a chunk of lanes at a
+// time when 32 rows do not fit the area.  `vec` (warp-uniform) = all 32 lanes hold a row and the range is 16-byte
+// aligned; otherwise every lane stores its own row element by element.
+template <typename OutT, typename SrcT>
+__device__ __forceinline__ void warp_store_rows(OutT *__restrict__ dst, const SrcT *vals, int dim, bool has_row, bool vec,
+                                                void *stage_area, int lane) {
+  constexpr int CAP = 640 / (int)sizeof(OutT), V = 16 / (int)sizeof(OutT);
+  int lpc = dim > 0 ? CAP / dim : 0;
+  if (lpc > 32) lpc = 32;
+  while (lpc > 0 && lpc < 32 && ((lpc * dim) % V)) lpc--;  // every chunk starts on a 16-byte boundary
+  if (!vec || lpc == 0) {
+    if (has_row)
+      for (int q = 0; q < dim; q++) __stcs(&dst[lane * dim + q], (OutT)vals[q]);
+    return;
+  }
+  OutT *stage = (OutT *)stage_area;
+#pragma unroll 1
+  for (int l0 = 0; l0 < 32; l0 += lpc) {
+    const int nl = (32 - l0) < lpc ? (32 - l0) : lpc, n = nl * dim;
+    if (lane >= l0 && lane < l0 + nl)
+      for (int q = 0; q < dim; q++) stage[(lane - l0) * dim + q] = (OutT)vals[q];
+    __syncwarp();
+    OutT *d = dst + l0 * dim;
+    const int nv = n / V;
+    for (int v = lane; v < nv; v += 32) __stcs((uint4 *)d + v, ((const uint4 *)stage)[v]);
+    for (int t = nv * V + lane; t < n; t += 32) __stcs(&d[t], stage[t]);
+    __syncwarp();
+  }
+}
+
 struct StepArgs {
   double *sf;
   int32_t *si;
@@ -161,6 +198,8 @@ struct StepArgs {
   uint8_t *done;
   int64_t N;
   int K;
+  unsigned vec;  // bit 0 observations, 1 rewards, 2 done: the buffer's rows can be written with 128-bit stores;
+                 // bit 3: the action buffer is 4-byte aligned (one 32-bit load per env when A == 4)
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -193,7 +232,7 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_step(const __grid_constant_
     load_env<L>(e, cold, k, a.sf, a.si, a.N, i);
   } else {
     e.base = env_smem_base(); e.boff = env_smem_offset(); e.cold = cold; e.stride = (int)blockDim.x;
-    e.err = 0; e.step = 0; e.masks_dirty = false;
+    e.err = 0; e.step = 0; e.masks_dirty = false; e.sq_watch = 0;
   }
   const int dim = obs_dim_of<E>(k.observer);
   const int A = k.n_actions;
@@ -203,12 +242,13 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_step(const __grid_constant_
     const int64_t row = (int64_t)s * a.N + i;
     unsigned cmd = 0;
     int n_cmd = 0;
+    bool bad_action = false;
     if (live) {
       if (k.discrete) {
         const uint8_t *ap = (const uint8_t *)a.actions + row * A;
         n_cmd = A;
         uint32_t w = 0;
-        if (A == 4) {  // one coalesced 32-bit load per env
+        if (A == 4 && (a.vec & 8u)) {  // one coalesced 32-bit load per env (4-byte aligned buffer)
           w = __ldcs((const uint32_t *)ap);  // streamed once: keep the L2 for the per-thread local arrays
         } else {
 #pragma unroll 1
@@ -217,7 +257,9 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_step(const __grid_constant_
 #pragma unroll
         for (int r = 0; r < R; r++) {
           int l, rt_;
-          thrust_from_direction((w >> (8 * r)) & 0xff, l, rt_);
+          const unsigned id = (w >> (8 * r)) & 0xff;
+          bad_action |= r < A && id > 7u;  // KeyError before anything moves (RR_EnvBase.py:593-606, :624)
+          thrust_from_direction((int)id, l, rt_);
           cmd |= pack_thrust(r, l, rt_);
         }
       } else {
@@ -230,16 +272,23 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_step(const __grid_constant_
       }
     }
     StepOut o;
-    sim_step(e, k, cmd, n_cmd, o, live);
+    sim_step(e, k, cmd, n_cmd, o, live && !bad_action);  // (every thread calls it: block-wide barriers inside)
+    if (bad_action) { o.step_err = RR_ERR_BAD_ACTION; e.err |= RR_ERR_BAD_ACTION; }
+    int done_flag = 0;
     if (live) {
       e.ret_h += o.rew_h; e.ret_g += o.rew_g;
       last_naughty = rr_popc(o.naughty);
-      st[RR_STAT_STEPS] += 1.0;
-      st[RR_STAT_NAUGHTY] += (double)last_naughty;
       const bool aborted = o.step_err != 0;
-      if (aborted) st[RR_STAT_ERRORS] += 1.0;
-      const int done = (o.done || aborted) ? 1 : 0;
-      if (done) {
+      done_flag = (o.done || aborted) ? 1 : 0;
+      // a step refused because the episode is over ("Game is over", :261-262; only without auto_reset) is not an
+      // env-step, not a new error and not another finished episode
+      const bool refused = (o.step_err & RR_ERR_STEP_AFTER_DONE) != 0;
+      if (!refused) {
+        st[RR_STAT_STEPS] += 1.0;
+        st[RR_STAT_NAUGHTY] += (double)last_naughty;
+        if (aborted) st[RR_STAT_ERRORS] += 1.0;
+      }
+      if (done_flag && !refused) {
         st[RR_STAT_EPISODES] += 1.0;
         st[RR_STAT_RETURN_HAPPY] += e.ret_h; st[RR_STAT_RETURN_GRUMPY] += e.ret_g;
         st[RR_STAT_LENGTH] += (double)e.step;
@@ -248,10 +297,22 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_step(const __grid_constant_
           reset_env(e, k, (uint64_t)(k.env_offset + i));
         }
       }
-      // results are written once and never read by this launch: streaming stores (evict-first) so that 100 MB of
-      // them per launch do not push the per-thread local arrays out of the L2
-      if (a.rew) { __stcs(&((OutT *)a.rew)[row * 2], (OutT)o.rew_h); __stcs(&((OutT *)a.rew)[row * 2 + 1], (OutT)o.rew_g); }
-      if (a.done) __stcs(&a.done[row], (unsigned char)done);
+    }
+    // Results: written once, never read back by this launch.  Every warp turns its 32 rows of each buffer into
+    // coalesced 128-bit streaming stores (warp_store_rows); all lanes of the warp take part (no divergence here).
+    {
+      const int lane = threadIdx.x & 31;
+      const bool full = __all_sync(0xffffffffu, live);  // padding lanes only exist in the batch's last warp
+      const int64_t row0 = row - lane;                 // the warp's first row
+      void *stage = (char *)(rr_smem + L::kTrigDoubles + E::kDoubles * (size_t)blockDim.x) + L::kStageBytes * (threadIdx.x >> 5);
+      if (a.rew) {
+        const double rw[2] = {o.rew_h, o.rew_g};
+        warp_store_rows<OutT>((OutT *)a.rew + row0 * 2, rw, 2, live, full && (a.vec & 2u), stage, lane);
+      }
+      if (a.done) {
+        const unsigned char dn[1] = {(unsigned char)done_flag};
+        warp_store_rows<unsigned char>(a.done + row0, dn, 1, live, full && (a.vec & 4u), stage, lane);
+      }
       if (dim > 0 && (a.obs_h || a.obs_g)) {
         double ob[kMaxObs];
         unsigned oerr = 0;
@@ -259,10 +320,8 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_step(const __grid_constant_
         for (int team = 1; team >= -1; team -= 2) {
           OutT *dst = (OutT *)(team > 0 ? a.obs_h : a.obs_g);
           if (!dst) continue;
-          observe(e, k, team, ob, oerr);
-          dst += row * dim;
-#pragma unroll 1
-          for (int q = 0; q < dim; q++) __stcs(&dst[q], (OutT)ob[q]);
+          if (live) observe(e, k, team, ob, oerr);
+          warp_store_rows<OutT>(dst + row0 * dim, ob, dim, live, full && (a.vec & 1u), stage, lane);
         }
       }
     }
@@ -391,7 +450,25 @@ struct rr_sim {
   cudaStream_t copy_stream = nullptr;  // rr_step_host: results of one chunk of steps travel while the next chunk runs
   cudaEvent_t chunk_done[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t launches = 0;
+  int host_chunks = 0;        // RR_HOST_CHUNKS at rr_create (0 = per-preset default)
+  bool host_zero_copy = true; // RR_HOST_ZEROCOPY=0 at rr_create forces the staged path
 };
+
+// Entry points run on the handle's device and leave the caller's current device as they found it.
+struct DeviceGuard {
+  int prev = -1;
+  bool good = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    good = (prev == dev) || cudaSetDevice(dev) == cudaSuccess;
+    if (prev == dev) prev = -1;  // nothing to restore
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  bool ok() const { return good; }
+};
+#define ON_DEVICE(dev)         \
+  DeviceGuard _guard(dev);     \
+  if (!_guard.ok()) return fail(RR_E_CUDA, "cudaSetDevice failed")
 
 static thread_local std::string g_err;
 const char *rr_last_error(void) { return g_err.c_str(); }
@@ -434,6 +511,21 @@ int rr_default_config(rr_config *c, int preset, const char *env_id) {
 using LGame = Launch<2, 2, 4, 4>;
 using LTrain = Launch<1, 0, 1, 0>;
 
+// Every kernel uses more than the default 48 KB of dynamic shared memory: opt in once per device (rr_create), not per
+// launch (the attribute call costs more than a K = 1 launch's own CPU time).
+template <class L>
+static cudaError_t opt_in_shared_memory() {
+  const int bytes = (int)L::smem_bytes(L::kMaxBlock);
+  cudaError_t e = cudaSuccess;
+  auto set = [&](auto kern) {
+    cudaError_t r = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) e = r;
+  };
+  set(k_step<L, float>); set(k_step<L, double>); set(k_init<L>); set(k_reset<L>); set(k_reset_fixed<L>);
+  set(k_observe<L, float>); set(k_observe<L, double>);
+  return e;
+}
+
 // Launch KERNEL<L, ...> for the handle's preset with the block size picked for its batch.
 #define LAUNCH_PRESET(s, st, KERNEL, ...)                                                                   \
   do {                                                                                                      \
@@ -441,13 +533,11 @@ using LTrain = Launch<1, 0, 1, 0>;
       using L = LGame;                                                                                      \
       auto kern = KERNEL;                                                                                   \
       const int blk = pick_block((s)->N, (s)->sms, L::kMaxBlock);                                           \
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem_bytes(L::kMaxBlock)); \
       kern<<<(unsigned)(((s)->N + blk - 1) / blk), blk, L::smem_bytes(blk), st>>>(__VA_ARGS__);             \
     } else {                                                                                                \
       using L = LTrain;                                                                                     \
       auto kern = KERNEL;                                                                                   \
       const int blk = pick_block((s)->N, (s)->sms, L::kMaxBlock);                                           \
-      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::smem_bytes(L::kMaxBlock)); \
       kern<<<(unsigned)(((s)->N + blk - 1) / blk), blk, L::smem_bytes(blk), st>>>(__VA_ARGS__);             \
     }                                                                                                       \
   } while (0)
@@ -467,13 +557,15 @@ int rr_create(const rr_config *cfg, int64_t n_envs, int device, rr_sim **out) {
   if (ce != cudaSuccess || ndev == 0)
     return fail(RR_E_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(ce));
   if (device < 0 || device >= ndev) return fail(RR_E_INVALID, "device index out of range");
-  CK(cudaSetDevice(device));
+  ON_DEVICE(device);
   rr_sim *s = new (std::nothrow) rr_sim();
   if (!s) return fail(RR_E_NOMEM, "host allocation failed");
   s->cfg = *cfg;
   s->k = make_consts(*cfg);
   s->N = n_envs;
   s->device = device;
+  if (const char *ev = getenv("RR_HOST_CHUNKS")) s->host_chunks = atoi(ev);
+  if (const char *ev = getenv("RR_HOST_ZEROCOPY")) s->host_zero_copy = atoi(ev) != 0;
   cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, device);
   if (s->sms <= 0) s->sms = 148;
   const bool game = cfg->preset == RR_PRESET_GAME;
@@ -490,18 +582,23 @@ int rr_create(const rr_config *cfg, int64_t n_envs, int device, rr_sim **out) {
     return fail(RR_E_NOMEM, "device allocation failed");
   }
   s->stats = s->own_stats;
-  CK(cudaMemset(s->stats, 0, sizeof(double) * RR_NUM_STATS));
+  {
+    cudaError_t ae = game ? opt_in_shared_memory<LGame>() : opt_in_shared_memory<LTrain>();
+    if (ae != cudaSuccess) { rr_destroy(s); return fail(RR_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ae)); }
+  }
+  if (cudaMemset(s->stats, 0, sizeof(double) * RR_NUM_STATS) != cudaSuccess) { rr_destroy(s); return fail(RR_E_CUDA, "cudaMemset failed"); }
   LAUNCH_PRESET(s, (cudaStream_t)0, (k_init<L>), s->k, s->sf, s->si, s->N, s->start);
   s->launches++;
-  CK(cudaGetLastError());
-  CK(cudaDeviceSynchronize());
+  cudaError_t le = cudaGetLastError();
+  if (le == cudaSuccess) le = cudaDeviceSynchronize();
+  if (le != cudaSuccess) { rr_destroy(s); return fail(RR_E_CUDA, std::string("k_init: ") + cudaGetErrorString(le)); }
   *out = s;
   return RR_OK;
 }
 
 int rr_destroy(rr_sim *s) {
   if (!s) return RR_OK;
-  cudaSetDevice(s->device);
+  DeviceGuard guard(s->device);
   cudaFree(s->sf); cudaFree(s->si); cudaFree(s->own_stats); cudaFree(s->start);
   cudaFree(s->d_act); cudaFree(s->d_obs_h); cudaFree(s->d_obs_g); cudaFree(s->d_rew); cudaFree(s->d_done);
   if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
@@ -580,7 +677,7 @@ __global__ void k_selftest_div(uint64_t seed, int64_t per_thread, unsigned long 
 
 int rr_selftest(int device, int which, int64_t n, uint64_t seed, int64_t *out2) {
   if (!out2 || n <= 0) return fail(RR_E_INVALID, "bad selftest arguments");
-  CK(cudaSetDevice(device));
+  ON_DEVICE(device);
   unsigned long long *d = nullptr;
   CK(cudaMalloc(&d, 2 * sizeof(unsigned long long)));
   CK(cudaMemset(d, 0, 2 * sizeof(unsigned long long)));
@@ -599,7 +696,7 @@ int rr_selftest(int device, int which, int64_t n, uint64_t seed, int64_t *out2) 
 
 int rr_reset(rr_sim *s, const uint8_t *mask_dev, void *stream) {
   if (!s) return fail(RR_E_INVALID, "null handle");
-  CK(cudaSetDevice(s->device));
+  ON_DEVICE(s->device);
   cudaStream_t st = (cudaStream_t)stream;
   LAUNCH_PRESET(s, st, (k_reset<L>), s->k, s->sf, s->si, s->N, mask_dev);
   s->launches++;
@@ -609,7 +706,7 @@ int rr_reset(rr_sim *s, const uint8_t *mask_dev, void *stream) {
 
 int rr_reset_fixed(rr_sim *s, const uint8_t *mask_dev, int32_t as_constructed, void *stream) {
   if (!s) return fail(RR_E_INVALID, "null handle");
-  CK(cudaSetDevice(s->device));
+  ON_DEVICE(s->device);
   cudaStream_t st = (cudaStream_t)stream;
   LAUNCH_PRESET(s, st, (k_reset_fixed<L>), s->k, s->sf, s->si, s->N, mask_dev, s->start, (int)as_constructed);
   s->launches++;
@@ -619,7 +716,7 @@ int rr_reset_fixed(rr_sim *s, const uint8_t *mask_dev, int32_t as_constructed, v
 
 int rr_set_starting_positions(rr_sim *s, const double *rob3, const double *ball2) {
   if (!s || !rob3 || !ball2) return fail(RR_E_INVALID, "null argument");
-  CK(cudaSetDevice(s->device));
+  ON_DEVICE(s->device);
   CK(cudaDeviceSynchronize());
   const int64_t N = s->N;
   const int R = s->R, B = s->B;
@@ -634,7 +731,7 @@ int rr_set_starting_positions(rr_sim *s, const double *rob3, const double *ball2
 
 int rr_get_starting_positions(rr_sim *s, double *rob3, double *ball2) {
   if (!s || !rob3 || !ball2) return fail(RR_E_INVALID, "null argument");
-  CK(cudaSetDevice(s->device));
+  ON_DEVICE(s->device);
   CK(cudaDeviceSynchronize());
   const int64_t N = s->N;
   const int R = s->R, B = s->B;
@@ -650,7 +747,7 @@ int rr_get_starting_positions(rr_sim *s, double *rob3, double *ball2) {
 int rr_observe(rr_sim *s, void *obs_h, void *obs_g, void *stream) {
   if (!s) return fail(RR_E_INVALID, "null handle");
   if (rr_obs_dim(s) == 0) return RR_OK;
-  CK(cudaSetDevice(s->device));
+  ON_DEVICE(s->device);
   cudaStream_t st = (cudaStream_t)stream;
   if (s->cfg.out_f64)
     LAUNCH_PRESET(s, st, (k_observe<L, double>), s->k, s->sf, s->si, s->N, obs_h, obs_g);
@@ -678,11 +775,20 @@ int rr_step(rr_sim *s, const void *actions, int32_t n_actions, int32_t k_steps, 
   int rc = check_actions(s, n_actions, k_steps);
   if (rc) return rc;
   if (n_actions > 0 && !actions) return fail(RR_E_INVALID, "actions is null");
-  CK(cudaSetDevice(s->device));
+  ON_DEVICE(s->device);
   cudaStream_t st = (cudaStream_t)stream;
   Consts k = s->k;
   k.n_actions = n_actions;
-  StepArgs a{s->sf, s->si, s->stats, actions, obs_h, obs_g, rew, done, s->N, k_steps};
+  // 128-bit result stores need 16-byte aligned buffers whose per-step rows are multiples of 16 bytes
+  const size_t osz = s->cfg.out_f64 ? 8 : 4;
+  auto rows16 = [&](const void *p, size_t row_bytes) { return (((uintptr_t)p) & 15u) == 0 && (row_bytes & 15u) == 0; };
+  unsigned vec = 0;
+  const size_t D = (size_t)rr_obs_dim(s);
+  if (rows16(obs_h, s->N * D * osz) && rows16(obs_g, s->N * D * osz)) vec |= 1u;
+  if (rows16(rew, s->N * 2 * osz)) vec |= 2u;
+  if (rows16(done, (size_t)s->N)) vec |= 4u;
+  if ((((uintptr_t)actions) & 3u) == 0) vec |= 8u;
+  StepArgs a{s->sf, s->si, s->stats, actions, obs_h, obs_g, rew, done, s->N, k_steps, vec};
   if (s->cfg.out_f64)
     LAUNCH_PRESET(s, st, (k_step<L, double>), k, a);
   else
@@ -701,18 +807,47 @@ static int ensure(void **p, size_t *cap, size_t need) {
   return RR_OK;
 }
 
+// device alias of a pinned (page-locked, mapped) host buffer, or null for pageable memory
+static void *pinned_alias(const void *host) {
+  if (!host) return nullptr;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
 int rr_step_host(rr_sim *s, const void *actions, int32_t n_actions, int32_t k_steps, void *obs_h, void *obs_g, void *rew,
                  uint8_t *done, void *stream) {
   if (!s) return fail(RR_E_INVALID, "null handle");
   int rc = check_actions(s, n_actions, k_steps);
   if (rc) return rc;
-  CK(cudaSetDevice(s->device));
+  ON_DEVICE(s->device);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t osz = s->cfg.out_f64 ? 8 : 4;
   const size_t rows = (size_t)k_steps * (size_t)s->N;
   const size_t act_b = rows * n_actions * (s->cfg.discrete ? 1 : 4);
   const size_t obs_b = rows * rr_obs_dim(s) * osz, rew_b = rows * 2 * osz, done_b = rows;
   if ((rc = ensure(&s->d_act, &s->cap_act, act_b ? act_b : 1))) return rc;
+  if (act_b) CK(cudaMemcpyAsync(s->d_act, actions, act_b, cudaMemcpyHostToDevice, st));
+
+  // Pinned result buffers: the kernel writes its rows straight into host memory (coalesced 128-bit streaming stores over
+  // PCIe / NVLink-C2C), so the device-to-host traffic overlaps the launch completely and nothing is staged in HBM.
+  if (s->host_zero_copy) {
+    void *a_oh = pinned_alias(obs_h), *a_og = pinned_alias(obs_g), *a_rw = pinned_alias(rew), *a_dn = pinned_alias(done);
+    const bool all_pinned = (!obs_h || !obs_b || a_oh) && (!obs_g || !obs_b || a_og) && (!rew || a_rw) && (!done || a_dn);
+    if (all_pinned) {
+      rc = rr_step(s, s->d_act, n_actions, k_steps, obs_b ? a_oh : nullptr, obs_b ? a_og : nullptr, a_rw, (uint8_t *)a_dn, stream);
+      if (rc) return rc;
+      CK(cudaStreamSynchronize(st));
+      return RR_OK;
+    }
+  }
+
+  // Pageable result buffers: staged in HBM and copied.  The K steps run as up to four launches of K/4 steps (same
+  // results: the state lives in HBM between launches); the device-to-host copies of one chunk's rows overlap the next
+  // chunk's kernel.  Outputs are [K][N][...], so a chunk of steps is one contiguous range of every buffer.  Every launch
+  // pays a fixed cost (state load / store, corner tables) and ends with its slowest env, so splitting only pays where the
+  // copies dominate: 4 chunks for the light TRAIN preset, 1 for GAME (profiles/README.md).  RR_HOST_CHUNKS (read once,
+  // at rr_create) overrides it.
   if ((rc = ensure(&s->d_obs_h, &s->cap_obs_h, obs_b ? obs_b : 1))) return rc;
   if ((rc = ensure(&s->d_obs_g, &s->cap_obs_g, obs_b ? obs_b : 1))) return rc;
   if ((rc = ensure(&s->d_rew, &s->cap_rew, rew_b))) return rc;
@@ -721,15 +856,7 @@ int rr_step_host(rr_sim *s, const void *actions, int32_t n_actions, int32_t k_st
     CK(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
     for (cudaEvent_t &e : s->chunk_done) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
-  if (act_b) CK(cudaMemcpyAsync(s->d_act, actions, act_b, cudaMemcpyHostToDevice, st));
-  // The K steps run as up to four launches of K/4 steps (same results: the state lives in HBM between launches);
-  // the device-to-host copies of one chunk's rows overlap the next chunk's kernel.  Outputs are [K][N][...], so a
-  // chunk of steps is one contiguous range of every buffer.
-  // Every launch pays a fixed cost (state load / store, corner tables) and ends with its slowest env, so splitting
-  // only pays where the copies dominate: 4 chunks for the light TRAIN preset (294 -> 345 M env-steps/s end to end),
-  // 1 for GAME (66.9 M; 2 chunks 63.5 M, 4 chunks 59.0 M: profiles/README.md).  RR_HOST_CHUNKS overrides it.
-  int chunks = s->R > 1 ? 1 : 4;
-  if (const char *ev = getenv("RR_HOST_CHUNKS")) chunks = atoi(ev);
+  int chunks = s->host_chunks > 0 ? s->host_chunks : (s->R > 1 ? 1 : 4);
   if (chunks > 4) chunks = 4;
   if (chunks < 1 || k_steps < chunks) chunks = 1;
   const size_t act_row = (size_t)s->N * n_actions * (s->cfg.discrete ? 1 : 4);
@@ -753,14 +880,13 @@ int rr_step_host(rr_sim *s, const void *actions, int32_t n_actions, int32_t k_st
   }
   CK(cudaStreamSynchronize(s->copy_stream));
   CK(cudaStreamSynchronize(st));
-  (void)obs_b; (void)rew_b; (void)done_b;
   return RR_OK;
 }
 
 int rr_set_state(rr_sim *s, const double *rob, const double *rhist, const int32_t *rflag, const double *ball,
                  const int32_t *step) {
   if (!s || !rob || !rhist || !rflag || !ball || !step) return fail(RR_E_INVALID, "null argument");
-  CK(cudaSetDevice(s->device));
+  ON_DEVICE(s->device);
   CK(cudaDeviceSynchronize());
   const int64_t N = s->N;
   const int R = s->R, B = s->B;
@@ -795,7 +921,7 @@ int rr_set_state(rr_sim *s, const double *rob, const double *rhist, const int32_
 
 int rr_get_state(rr_sim *s, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step) {
   if (!s || !rob || !rhist || !rflag || !ball || !step) return fail(RR_E_INVALID, "null argument");
-  CK(cudaSetDevice(s->device));
+  ON_DEVICE(s->device);
   CK(cudaDeviceSynchronize());
   const int64_t N = s->N;
   const int R = s->R, B = s->B;
@@ -827,7 +953,7 @@ int rr_get_state(rr_sim *s, double *rob, double *rhist, int32_t *rflag, double *
 
 int rr_error_mask(rr_sim *s, uint32_t *err_host, int32_t clear) {
   if (!s || !err_host) return fail(RR_E_INVALID, "null argument");
-  CK(cudaSetDevice(s->device));
+  ON_DEVICE(s->device);
   CK(cudaDeviceSynchronize());
   int32_t *p = s->si + (size_t)(s->R + 2) * s->N;
   CK(cudaMemcpy(err_host, p, sizeof(uint32_t) * s->N, cudaMemcpyDeviceToHost));
@@ -837,7 +963,7 @@ int rr_error_mask(rr_sim *s, uint32_t *err_host, int32_t clear) {
 
 int rr_last_naughty(rr_sim *s, int32_t *count_host) {
   if (!s || !count_host) return fail(RR_E_INVALID, "null argument");
-  CK(cudaSetDevice(s->device));
+  ON_DEVICE(s->device);
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(count_host, s->si + (size_t)(s->R + 3) * s->N, sizeof(int32_t) * s->N, cudaMemcpyDeviceToHost));
   return RR_OK;
@@ -845,7 +971,7 @@ int rr_last_naughty(rr_sim *s, int32_t *count_host) {
 
 int rr_get_stats(rr_sim *s, double *stats_host) {
   if (!s || !stats_host) return fail(RR_E_INVALID, "null argument");
-  CK(cudaSetDevice(s->device));
+  ON_DEVICE(s->device);
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(stats_host, s->stats, sizeof(double) * RR_NUM_STATS, cudaMemcpyDeviceToHost));
   return RR_OK;
@@ -859,7 +985,7 @@ int rr_stats_device_ptr(rr_sim *s, double **p) {
 
 int rr_clear_stats(rr_sim *s, void *stream) {
   if (!s) return fail(RR_E_INVALID, "null handle");
-  CK(cudaSetDevice(s->device));
+  ON_DEVICE(s->device);
   CK(cudaMemsetAsync(s->stats, 0, sizeof(double) * RR_NUM_STATS, (cudaStream_t)stream));
   return RR_OK;
 }

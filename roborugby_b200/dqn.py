@@ -6,6 +6,9 @@ Mirror of the reference's agent (Training_DQN_pytorch.py:25-197) with everything
     DeepQNetwork obs -> 256 -> 256 -> n_actions  :25-67       same module (torch.nn; library GEMMs are fine here:
                                                              the hot path of this repo is the env, not this MLP)
     store_transition(s, a, r, s_, done)          :119-128     store(s, a, r, s_, done) for N transitions at once
+    main loop: happy AND grumpy transition       :317-377     train(): both teams' transitions stored per step, happy
+      stored per step, only the happy action                  first; only the happy action applied (drive_grumpy=True
+      applied (:343)                                          also applies the grumpy one)
     choose_action: eps-greedy, one forward       :130-141     choose_actions(obs [N, D]) -> uint8 [N]
     learn(): uniform batch without replacement,  :143-189     learn(): identical target r + gamma * max Q_target(s_)
       q_next[terminal] = 0, MSE, Adam,                        (terminal rows zeroed), MSE, Adam, hard target copy
@@ -110,26 +113,51 @@ class VecDQNAgent:
         return loss.detach()
 
 
-def train(env, agent, n_steps, learn_every=1, log_every=0):
-    """The reference's main loop (Training_DQN_pytorch.py:317-377) for N envs in lockstep: the agent drives
-    the first happy robot of every env (`env.step([action])`, :341), other robots keep zero thrust.
+def train(env, agent, n_steps, learn_every=1, log_every=0, drive_grumpy=False):
+    """The reference's main loop (Training_DQN_pytorch.py:317-377) for N envs in lockstep.
+
+    Per iteration, exactly as the reference does per env: an eps-greedy action for the happy observation (:333-336)
+    and, when the env has grumpy robots, one for the grumpy observation (:338-339); `env.step([action])` (:343 — the
+    reference computes the grumpy action but passes only the happy one, the rest of the list is commented out);
+    BOTH transitions are stored, happy first (:351-353: the grumpy one holds the action that was chosen for it, the
+    grumpy reward `info.dblGrumpyScore` and next state `info.adblGrumpyState`, and the same done flag); then learn().
+
+    drive_grumpy=True is the loop with the commented-out part of :343 restored: the grumpy action is also applied, to
+    the first grumpy robot (robot index num_robots_happy; robots between the two get uniformly random actions, since
+    a GameEnv_Simple command list cannot skip a robot, RR_EnvBase.py:617-626).
 
     Returns a dict with env-steps/s measured with CUDA events around the whole loop."""
+    N = env.num_envs
+    has_grumpy = env.preset.num_robots_grumpy > 0
+    g0 = env.preset.num_robots_happy          # index of the first grumpy robot
     obs = env.reset().clone()
+    obs_g = env.observe()[1].clone() if has_grumpy else None   # get_game_state(int_team=TEAM_GRUMPY), :322
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     losses = []
     ev0.record()
     for it in range(n_steps):
         act = agent.choose_actions(obs)
-        obs_, rew, done, _ = env.step(act.view(-1, 1))
+        act_g = agent.choose_actions(obs_g) if has_grumpy else None
+        if has_grumpy and drive_grumpy:
+            cmd = torch.randint(0, agent.n_actions, (N, g0 + 1), device=agent.device, generator=agent.gen).to(torch.uint8)
+            cmd[:, 0] = act
+            cmd[:, g0] = act_g
+        else:
+            cmd = act.view(-1, 1)
+        obs_, rew, done, info = env.step(cmd)
         agent.store(obs, act, rew, obs_, done)
+        if has_grumpy:
+            agent.store(obs_g, act_g, info["reward_grumpy"], info["obs_grumpy"], done)
         if (it + 1) % learn_every == 0:
             loss = agent.learn()
             if loss is not None and log_every and (it + 1) % log_every == 0:
                 losses.append(float(loss))
         obs = obs_.clone()
+        if has_grumpy:
+            obs_g = info["obs_grumpy"].clone()
     ev1.record()
     torch.cuda.synchronize()
     secs = ev0.elapsed_time(ev1) * 1e-3
-    return {"env_steps": n_steps * env.num_envs, "seconds": secs, "env_steps_per_s": n_steps * env.num_envs / secs,
+    return {"env_steps": n_steps * N, "seconds": secs, "env_steps_per_s": n_steps * N / secs,
+            "transitions": n_steps * N * (2 if has_grumpy else 1),
             "losses": losses, "epsilon": agent.epsilon, "stats": env.get_stats()}

@@ -52,6 +52,8 @@ def lib():
         L.emul_predicates.restype = None
         L.emul_last_replays.argtypes = []
         L.emul_last_replays.restype = C.c_double
+        L.emul_last_whole_frames.argtypes = []
+        L.emul_last_whole_frames.restype = C.c_double
         _lib = L
     return _lib
 

@@ -16,7 +16,7 @@ struct HostEnv {
   double buf[E::kDoubles];
   double cold[E::kColdDoubles];
   E e;
-  HostEnv() { std::memset(buf, 0, sizeof buf); std::memset(cold, 0, sizeof cold); e.base = buf; e.cold = cold; e.stride = 1; e.trig = &kSinCosHost[0][0]; e.thrust = 0x88888888u; e.hvalid = 0; e.step = 0; e.err = 0; e.episode = 0; e.ret_h = e.ret_g = 0; }
+  HostEnv() { std::memset(buf, 0, sizeof buf); std::memset(cold, 0, sizeof cold); e.base = buf; e.cold = cold; e.stride = 1; e.trig = &kSinCosHost[0][0]; e.thrust = 0x88888888u; e.hvalid = 0; e.step = 0; e.err = 0; e.episode = 0; e.ret_h = e.ret_g = 0; e.sq_watch = 0; e.masks_dirty = true; e.br_near = e.bb_near = e.rr_near = e.wall_near = e.moving = 0; }
 };
 
 template <class E>
@@ -42,6 +42,7 @@ static void load(E &e, const Consts &k, const double *rob, const double *rhist, 
   e.step = step; e.err = 0; e.episode = 0; e.ret_h = e.ret_g = 0;
   e.invalidate_caches();
   e.memo_clear();
+  e.sq_watch = 0;
 }
 
 template <class E>
@@ -62,6 +63,7 @@ static void store(const E &e, double *rob, double *rhist, int32_t *rflag, double
 }
 
 static double g_last_replays = 0.0;  // frames of the last emul_step answered by the squeeze memo
+static double g_last_whole = 0.0;    // ... of which whole frames
 
 template <int NH, int NG, int NP, int NN>
 static unsigned step_t(const Consts &k, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,
@@ -88,6 +90,7 @@ static unsigned step_t(const Consts &k, double *rob, double *rhist, int32_t *rfl
   StepOut o;
   sim_step(e, k, cmd, n_cmd, o, true);
   g_last_replays = e.mm(kMReplays);
+  g_last_whole = e.mm(kMFrames);
   unsigned oerr = 0;
   if (obs_h) observe(e, k, 1, obs_h, oerr);
   if (obs_g) observe(e, k, -1, obs_g, oerr);
@@ -115,6 +118,7 @@ static unsigned reset_t(const Consts &k, double *rob, double *rhist, int32_t *rf
 extern "C" {
 
 double emul_last_replays(void) { return g_last_replays; }
+double emul_last_whole_frames(void) { return g_last_whole; }
 
 unsigned emul_step(const rr_config *cfg, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,
                    const double *actions, int n_actions, double *obs_h, double *obs_g, double *rew, int32_t *done,

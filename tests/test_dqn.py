@@ -87,6 +87,55 @@ def test_dqn_loop_runs_on_gpu_vec_env():
     assert out["stats"]["steps"] == 40 * 512
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("drive_grumpy", [False, True])
+def test_dqn_replay_holds_both_teams_transitions_of_the_oracle(oracle, drive_grumpy):
+    """Training_DQN_pytorch.py:333-353 on the GAME preset (which has grumpy robots): per step the replay receives the
+    happy transition and then the grumpy one (its own observation, the action chosen for it, info.dblGrumpyScore,
+    info.adblGrumpyState, the same done).  The stored rows of a few envs are replayed on the oracle from the env's
+    own initial state with the stored actions."""
+    import numpy as np
+    from roborugby_b200.dqn import train
+    from roborugby_b200.vec_env import RoboRugbyVecEnv
+    V2, N, T, seed = "RoboRugbySimpleDuel-v2", 48, 6, 21
+    env = RoboRugbyVecEnv(V2, N, preset="GAME", device="cuda:0", seed=seed, n_actions=1)
+    ag = VecDQNAgent(env.obs_dim, batch_size=4 * N, max_mem_size=4 * N * T, epsilon=1.0, eps_end=1.0, device="cuda:0", seed=3)
+    out = train(env, ag, T, drive_grumpy=drive_grumpy)
+    assert ag.mem_cntr == 2 * N * T and out["transitions"] == 2 * N * T
+    S, S_, A = ag.state_memory.cpu().numpy(), ag.new_state_memory.cpu().numpy(), ag.action_memory.cpu().numpy()
+    Rw, Tm = ag.reward_memory.cpu().numpy(), ag.terminal_memory.cpu().numpy()
+    # the random middle-robot actions of drive_grumpy come from the agent's generator: recover them from the env is not
+    # possible, so that mode is checked on the rows that do not depend on them (observations before the first step,
+    # layout, dones) and the faithful mode on everything
+    oracle.scratch_mode(1)
+    try:
+        for i in range(0, N, 5):
+            o = oracle.OracleEnv("GAME", V2, time_limit=True)
+            o.reset_philox(seed, i, 0)     # rr_create
+            o.reset_philox(seed, i, 1)     # env.reset() in train()
+            for t in range(T):
+                h, g = 2 * N * t + i, 2 * N * t + N + i
+                oh, og = o.observe(1), o.observe(-1)
+                if t == 0 or not drive_grumpy:
+                    assert np.allclose(S[h], oh.astype(np.float32), rtol=1e-6, atol=1e-6), (i, t)
+                    assert np.allclose(S[g], og.astype(np.float32), rtol=1e-6, atol=1e-6), (i, t)
+                if drive_grumpy:
+                    break
+                r = o.step([A[h]])          # only the happy action is applied (:343)
+                assert Tm[h] == Tm[g] == bool(r["done"])
+                assert np.allclose(Rw[h], r["rew"][0], rtol=1e-5, atol=1e-6) and np.allclose(Rw[g], r["rew"][1], rtol=1e-5, atol=1e-6)
+                assert np.allclose(S_[h], r["obs_h"].astype(np.float32), rtol=1e-6, atol=1e-6), (i, t)
+                assert np.allclose(S_[g], r["obs_g"].astype(np.float32), rtol=1e-6, atol=1e-6), (i, t)
+                assert 0 <= A[g] < 8
+    finally:
+        oracle.scratch_mode(0)
+    if drive_grumpy:   # the grumpy robot really moves: its thrust is the commanded direction's
+        st = env.get_state()
+        assert (st["rflag"][:, env.preset.num_robots_happy, :2] != 0).any()
+    else:              # reference behaviour: nothing but robot 0 is ever commanded
+        assert (env.get_state()["rflag"][:, 1:, :2] == 0).all()
+
+
 def test_og_twitchy_action_distribution():
     """Batched OG_Twitchy (RR_Players.py:14-30): 5 % left, 45 % forward, 45 % back, 5 % right, as GameEnv_Simple ids."""
     import torch

@@ -560,14 +560,24 @@ def test_gpu_squeeze_memo_replay_is_exact(oracle, preset):
     and with RR_FLAG_NO_SQUEEZE_MEMO: every output row and the final state must be bit-identical, the memo must have
     answered most of the pinned frames (RR_STAT_REPLAYS), and a sample is checked against the oracle."""
     from roborugby_b200 import _lib
-    from squeeze_util import actions, oracle_env, scenario
+    from squeeze_util import actions, oracle_env, pincer_env, scenario
     rng = np.random.default_rng(5)
     N, K = 1536, 6
     states, acts = [], []
     for i in range(N):
-        o = oracle_env(oracle, preset, scenario(rng, preset))
+        if preset == "GAME" and i % 4 == 3:      # pinned between two robots
+            o = pincer_env(oracle, rng)
+            a = actions(rng, o.R, K)
+            a[:, 1] = a[:, 0]
+        else:                                     # pinned against a wall, every third one with a bystander ball nearby
+            spect = None
+            if i % 3 == 1:
+                ang, d = rng.uniform(0, 2 * np.pi), rng.uniform(16, 60)
+                spect = [(d * np.cos(ang), d * np.sin(ang))]
+            o = oracle_env(oracle, preset, scenario(rng, preset), spectators=spect)
+            a = actions(rng, o.R, K)
         states.append(o.get_state())
-        acts.append(actions(rng, o.R, K))
+        acts.append(a)
     pool = {k: np.stack([s[k] for s in states]) for k in STATE_KEYS}
     a = torch.as_tensor(np.stack(acts, 1)).cuda()          # [K, N, R]
     res = []

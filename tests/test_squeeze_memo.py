@@ -25,7 +25,7 @@ def test_squeeze_memo_replay_is_exact(oracle, seed):
     from emul.emul import EmulEnv
     from roborugby_b200 import _lib
     rng = np.random.default_rng(seed)
-    failed = replays = 0
+    failed = replays = whole = 0
     oracle.scratch_mode(1)
     emul.use_libm_sincos(True)
     try:
@@ -54,6 +54,7 @@ def test_squeeze_memo_replay_is_exact(oracle, seed):
             for a in acts:
                 r_on = on.step(a)
                 replays += emul.lib().emul_last_replays()
+                whole += emul.lib().emul_last_whole_frames()
                 r_off = off.step(a)
                 r_o = o.step(a)
                 s_on, s_off, s_o = on.get_state(), off.get_state(), o.get_state()
@@ -74,7 +75,9 @@ def test_squeeze_memo_replay_is_exact(oracle, seed):
     finally:
         emul.use_libm_sincos(False)
         oracle.scratch_mode(0)
-    print(f"seed {seed}: {failed} pinned-ball frames in the oracle, {int(replays)} replayed by the memo")
+    print(f"seed {seed}: {failed} pinned-ball frames in the oracle, {int(replays)} replayed by the memo, "
+          f"{int(whole)} of them as whole frames")
+    assert whole > 0.5 * replays
     assert failed > (1500 if seed < 3 else 200) and replays > (0.7 if seed < 2 else 0.4) * failed
 
 
