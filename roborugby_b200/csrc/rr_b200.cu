@@ -82,7 +82,7 @@ __device__ __forceinline__ void load_env(typename L::E &e, double *cold, const C
   e.cold = cold;
   e.stride = (int)blockDim.x;
   e.memo_clear();
-  e.sq_watch = 0;
+  e.sq_watch = 0; e.rr_stuck = 0;
   int f = 0;
   e.hvalid = 0;
   e.thrust = 0;
@@ -232,7 +232,7 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_step(const __grid_constant_
     load_env<L>(e, cold, k, a.sf, a.si, a.N, i);
   } else {
     e.base = env_smem_base(); e.boff = env_smem_offset(); e.cold = cold; e.stride = (int)blockDim.x;
-    e.err = 0; e.step = 0; e.masks_dirty = false; e.sq_watch = 0;
+    e.err = 0; e.step = 0; e.masks_dirty = false; e.sq_watch = 0; e.rr_stuck = 0;
   }
   const int dim = obs_dim_of<E>(k.observer);
   const int A = k.n_actions;

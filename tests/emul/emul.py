@@ -50,10 +50,14 @@ def lib():
         L.emul_sincos2.restype = None
         L.emul_predicates.argtypes = [C.POINTER(Config), vp, vp, vp, vp, vp, vp, vp]
         L.emul_predicates.restype = None
+        L.emul_step_k.argtypes = [C.POINTER(Config), vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]
+        L.emul_step_k.restype = C.c_uint
         L.emul_last_replays.argtypes = []
         L.emul_last_replays.restype = C.c_double
         L.emul_last_whole_frames.argtypes = []
         L.emul_last_whole_frames.restype = C.c_double
+        L.emul_last_stuck_replays.argtypes = []
+        L.emul_last_stuck_replays.restype = C.c_double
         _lib = L
     return _lib
 
@@ -87,6 +91,16 @@ class EmulEnv:
                               _p(self.stepc), _p(a), a.size, _p(oh), _p(og), _p(rew), _p(done), _p(ng))
         return dict(obs_h=oh[:self.obs_dim], obs_g=og[:self.obs_dim], rew=rew, done=int(done[0]), naughty=int(ng[0]),
                     err=int(err))
+
+    def step_k(self, actions):
+        """K discrete steps on one Env object (memo state persists across the steps, as in a fused GPU launch).
+        actions [K, A]; returns (error bits, rewards [K, 2], (replays, whole-frame replays, stuck-pair replays))."""
+        a = np.ascontiguousarray(np.asarray(actions, np.float64))
+        K, A = a.shape
+        rew = np.zeros((K, 2)); cnt = np.zeros(3)
+        err = lib().emul_step_k(C.byref(self.cfg), _p(self.rob), _p(self.rhist), _p(self.rflag), _p(self.ball),
+                                _p(self.stepc), _p(a), A, K, _p(rew), _p(cnt))
+        return int(err), rew, cnt
 
     def reset(self, env_index, episode, construct=False):
         return lib().emul_reset(C.byref(self.cfg), _p(self.rob), _p(self.rhist), _p(self.rflag), _p(self.ball),

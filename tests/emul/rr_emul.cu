@@ -16,7 +16,7 @@ struct HostEnv {
   double buf[E::kDoubles];
   double cold[E::kColdDoubles];
   E e;
-  HostEnv() { std::memset(buf, 0, sizeof buf); std::memset(cold, 0, sizeof cold); e.base = buf; e.cold = cold; e.stride = 1; e.trig = &kSinCosHost[0][0]; e.thrust = 0x88888888u; e.hvalid = 0; e.step = 0; e.err = 0; e.episode = 0; e.ret_h = e.ret_g = 0; e.sq_watch = 0; e.masks_dirty = true; e.br_near = e.bb_near = e.rr_near = e.wall_near = e.moving = 0; }
+  HostEnv() { std::memset(buf, 0, sizeof buf); std::memset(cold, 0, sizeof cold); e.base = buf; e.cold = cold; e.stride = 1; e.trig = &kSinCosHost[0][0]; e.thrust = 0x88888888u; e.hvalid = 0; e.step = 0; e.err = 0; e.episode = 0; e.ret_h = e.ret_g = 0; e.sq_watch = 0; e.rr_stuck = 0; e.masks_dirty = true; e.br_near = e.bb_near = e.rr_near = e.wall_near = e.moving = 0; }
 };
 
 template <class E>
@@ -42,7 +42,7 @@ static void load(E &e, const Consts &k, const double *rob, const double *rhist, 
   e.step = step; e.err = 0; e.episode = 0; e.ret_h = e.ret_g = 0;
   e.invalidate_caches();
   e.memo_clear();
-  e.sq_watch = 0;
+  e.sq_watch = 0; e.rr_stuck = 0;
 }
 
 template <class E>
@@ -64,6 +64,7 @@ static void store(const E &e, double *rob, double *rhist, int32_t *rflag, double
 
 static double g_last_replays = 0.0;  // frames of the last emul_step answered by the squeeze memo
 static double g_last_whole = 0.0;    // ... of which whole frames
+static double g_last_stuck = 0.0;    // robot-robot phases answered by the stuck-pair memo
 
 template <int NH, int NG, int NP, int NN>
 static unsigned step_t(const Consts &k, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,
@@ -91,6 +92,7 @@ static unsigned step_t(const Consts &k, double *rob, double *rhist, int32_t *rfl
   sim_step(e, k, cmd, n_cmd, o, true);
   g_last_replays = e.mm(kMReplays);
   g_last_whole = e.mm(kMFrames);
+  g_last_stuck = e.mm(kMStuckReplays);
   unsigned oerr = 0;
   if (obs_h) observe(e, k, 1, obs_h, oerr);
   if (obs_g) observe(e, k, -1, obs_g, oerr);
@@ -99,6 +101,34 @@ static unsigned step_t(const Consts &k, double *rob, double *rhist, int32_t *rfl
   *naughty = rr_popc(o.naughty);
   store(e, rob, rhist, rflag, ball, step);
   return o.step_err;
+}
+
+// K discrete env-steps in one call on ONE Env object: like a fused GPU launch, the per-thread memo state (squeeze
+// memo, stuck-pair memo) lives across the steps.  Returns the OR of the steps' error bits; stops at the first error.
+template <int NH, int NG, int NP, int NN>
+static unsigned step_k_t(const Consts &k, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,
+                         const double *actions, int n_actions, int K, double *rew_out, double *counters) {
+  HostEnv<NH, NG, NP, NN> h;
+  auto &e = h.e;
+  using E = typename HostEnv<NH, NG, NP, NN>::E;
+  load(e, k, rob, rhist, rflag, ball, *step);
+  unsigned errs = 0;
+  for (int s = 0; s < K; s++) {
+    unsigned cmd = 0;
+    for (int r = 0; r < n_actions && r < E::R; r++) {
+      int l, rt;
+      thrust_from_direction((int)actions[s * n_actions + r], l, rt);
+      cmd |= pack_thrust(r, l, rt);
+    }
+    StepOut o;
+    sim_step(e, k, cmd, n_actions, o, true);
+    rew_out[2 * s] = o.rew_h; rew_out[2 * s + 1] = o.rew_g;
+    errs |= o.step_err;
+    if (o.step_err) break;
+  }
+  counters[0] = e.mm(kMReplays); counters[1] = e.mm(kMFrames); counters[2] = e.mm(kMStuckReplays);
+  store(e, rob, rhist, rflag, ball, step);
+  return errs;
 }
 
 template <int NH, int NG, int NP, int NN>
@@ -119,6 +149,7 @@ extern "C" {
 
 double emul_last_replays(void) { return g_last_replays; }
 double emul_last_whole_frames(void) { return g_last_whole; }
+double emul_last_stuck_replays(void) { return g_last_stuck; }
 
 unsigned emul_step(const rr_config *cfg, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,
                    const double *actions, int n_actions, double *obs_h, double *obs_g, double *rew, int32_t *done,
@@ -128,6 +159,15 @@ unsigned emul_step(const rr_config *cfg, double *rob, double *rhist, int32_t *rf
   if (cfg->preset == RR_PRESET_GAME)
     return step_t<2, 2, 4, 4>(k, rob, rhist, rflag, ball, step, actions, n_actions, obs_h, obs_g, rew, done, naughty);
   return step_t<1, 0, 1, 0>(k, rob, rhist, rflag, ball, step, actions, n_actions, obs_h, obs_g, rew, done, naughty);
+}
+
+unsigned emul_step_k(const rr_config *cfg, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,
+                     const double *actions, int n_actions, int K, double *rew_out, double *counters) {
+  Consts k = make_consts(*cfg);
+  k.n_actions = n_actions;
+  if (cfg->preset == RR_PRESET_GAME)
+    return step_k_t<2, 2, 4, 4>(k, rob, rhist, rflag, ball, step, actions, n_actions, K, rew_out, counters);
+  return step_k_t<1, 0, 1, 0>(k, rob, rhist, rflag, ball, step, actions, n_actions, K, rew_out, counters);
 }
 
 unsigned emul_reset(const rr_config *cfg, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,

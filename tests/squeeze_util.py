@@ -60,6 +60,24 @@ def pincer_env(oracle, rng, time_limit=False):
     return o
 
 
+def stuck_pair_env(oracle, rng, time_limit=False):
+    """GAME preset: robots 0 and 1 a few pixels apart, facing each other (or at an angle), no ball near: driving at
+    each other they collide and are both undone, frame after frame (RR_EnvBase.py:303-333)."""
+    o = oracle.OracleEnv("GAME", V2, time_limit=time_limit)
+    x0, y0 = rng.uniform(150, 650), rng.uniform(150, 650)
+    ang = rng.uniform(0, 360)
+    ca, sa = np.cos(np.radians(ang)), -np.sin(np.radians(ang))
+    g = rng.uniform(10.5, 14)                                       # half the centre distance (robots are 20 long)
+    j = rng.uniform(-15, 15)
+    rob3 = [(x0 - g * ca, y0 - g * sa, (ang + rng.uniform(-25, 25)) % 360),
+            (x0 + g * ca - j * sa, y0 + g * sa + j * ca, (ang + 180 + rng.uniform(-25, 25)) % 360),
+            (60.0 + 680 * (x0 < 400), 70.0, 45.0), (60.0 + 680 * (x0 < 400), 730.0, 135.0)]
+    ball2 = [(50.0 + 95 * i, 45.0 + 710 * (y0 < 400)) for i in range(o.B)]
+    o.set_starting_positions(np.array(rob3, float), np.array(ball2, float))
+    o.reset_draws([], randomize=False)
+    return o
+
+
 def actions(rng, n_robots, n_steps=6):
     """Robot 0 keeps pushing forward (with one random action in between); the others move at random."""
     lead = [0, 0, 0, int(rng.integers(0, 8)), 0, 0][:n_steps]

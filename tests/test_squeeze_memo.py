@@ -7,7 +7,7 @@ Also pins the relaxed reset placement (strict_reset = 0) of the kernels against 
 import numpy as np
 import pytest
 
-from squeeze_util import V2, actions, oracle_env, pincer_env, scenario
+from squeeze_util import V2, actions, oracle_env, pincer_env, scenario, stuck_pair_env
 
 
 def _cfg(preset, flags):
@@ -79,6 +79,147 @@ def test_squeeze_memo_replay_is_exact(oracle, seed):
           f"{int(whole)} of them as whole frames")
     assert whole > 0.5 * replays
     assert failed > (1500 if seed < 3 else 200) and replays > (0.7 if seed < 2 else 0.4) * failed
+
+
+def test_stuck_pair_memo_replay_is_exact(oracle):
+    """Two robots driving into each other (both undone every frame, RR_EnvBase.py:303-333): the stuck-pair memo of
+    rr_sim.cuh (resolve_bot_collisions / stuck_pair_replay) on, off, and the oracle."""
+    from emul import emul
+    from emul.emul import EmulEnv
+    from roborugby_b200 import _lib
+    rng = np.random.default_rng(11)
+    replays = naughty = raised = 0
+    oracle.scratch_mode(1)
+    emul.use_libm_sincos(True)
+    try:
+        for it in range(80):
+            o = stuck_pair_env(oracle, rng)
+            st0 = o.get_state()
+            on = EmulEnv(_cfg("GAME", 0), o.R, o.B, 5)
+            off = EmulEnv(_cfg("GAME", _lib.FLAG_NO_SQUEEZE_MEMO), o.R, o.B, 5)
+            on.set_state(st0); off.set_state(st0)
+            for s in range(6):
+                a = [int(x) for x in rng.integers(0, 8, o.R)]
+                if s in (0, 1, 4):
+                    a[0] = a[1] = 0          # both forward: head-on
+                r_on = on.step(a)
+                replays += emul.lib().emul_last_stuck_replays()
+                r_off = off.step(a)
+                r_o = o.step(a)
+                assert r_on["err"] == r_off["err"] == r_o["err"]
+                if r_on["err"]:
+                    raised += 1
+                    break
+                s_on, s_off, s_o = on.get_state(), off.get_state(), o.get_state()
+                for k in s_on:
+                    assert np.array_equal(s_on[k], s_off[k]), (it, s, k)
+                assert np.array_equal(r_on["rew"], r_off["rew"]) and r_on["naughty"] == r_off["naughty"] == r_o["naughty"]
+                naughty += r_o["naughty"]
+                for k in ("rflag", "step"):
+                    assert np.array_equal(s_on[k], s_o[k]), (it, s, k)
+                for k in ("rob", "rhist", "ball"):
+                    assert np.allclose(s_on[k], s_o[k], rtol=1e-9, atol=1e-9), (it, s, k)
+                assert np.allclose(r_on["rew"], r_o["rew"], rtol=1e-9, atol=1e-9)
+    finally:
+        emul.use_libm_sincos(False)
+        oracle.scratch_mode(0)
+    print(f"stuck pairs: {naughty} naughty robot-steps, {int(replays)} robot-robot phases replayed, {raised} scenarios raised")
+    assert replays > 1000 and naughty > 300
+
+
+def _mixed_scenario(oracle, rng, i, preset, K):
+    """The scenario mix of the GPU test (tests/test_parity_gpu.py::test_gpu_squeeze_memo_replay_is_exact)."""
+    if preset == "GAME" and i % 4 == 3:
+        o = pincer_env(oracle, rng)
+        a = actions(rng, o.R, K)
+        a[:, 1] = a[:, 0]
+    elif preset == "GAME" and i % 4 == 2:
+        o = stuck_pair_env(oracle, rng)
+        a = actions(rng, o.R, K)
+        a[:, 1] = a[:, 0]
+    else:
+        spect = None
+        if i % 3 == 1:
+            ang, d = rng.uniform(0, 2 * np.pi), rng.uniform(16, 60)
+            spect = [(d * np.cos(ang), d * np.sin(ang))]
+        o = oracle_env(oracle, preset, scenario(rng, preset), spectators=spect)
+        a = actions(rng, o.R, K)
+    return o, a
+
+
+@pytest.mark.parametrize("preset", ["GAME", "TRAIN"])
+def test_memos_persist_across_fused_steps_exactly(oracle, preset):
+    """Inside a fused launch the memo state outlives the env-step (slots recorded under one action are hit again when
+    the action comes back, whole-frame records are replayed across the step boundary).  emul_step_k runs K steps on
+    one Env object like a launch does: memo on == memo off bit for bit, and == the oracle within 1e-9, on the GPU
+    test's scenario mix (wall squeezes with and without a bystander ball, two-robot pincers, robot pairs stuck on
+    each other).  A bystander that is itself at the wall found a real bug here: its own wall bounce carried it into
+    the pushing robot, so whole frames are only replayed when nothing else is in contact."""
+    from emul import emul
+    from emul.emul import EmulEnv
+    from roborugby_b200 import _lib
+    rng = np.random.default_rng(5)
+    K, n = 6, 700 if preset == "GAME" else 300
+    tot = np.zeros(3)
+    oracle.scratch_mode(1)
+    emul.use_libm_sincos(True)
+    try:
+        for i in range(n):
+            o, a = _mixed_scenario(oracle, rng, i, preset, K)
+            st0 = o.get_state()
+            on = EmulEnv(_cfg(preset, 0), o.R, o.B, 5)
+            off = EmulEnv(_cfg(preset, _lib.FLAG_NO_SQUEEZE_MEMO), o.R, o.B, 5)
+            on.set_state(st0); off.set_state(st0)
+            e_on, r_on, cnt = on.step_k(a)
+            e_off, r_off, cnt_off = off.step_k(a)
+            tot += cnt
+            assert not cnt_off.any()
+            s_on, s_off = on.get_state(), off.get_state()
+            assert e_on == e_off and np.array_equal(r_on, r_off), i
+            for k in s_on:
+                assert np.array_equal(s_on[k], s_off[k]), (i, k)
+            if i % 7 == 0 and not e_on:
+                for t in range(K):
+                    r = o.step(a[t])
+                    assert not r["err"] and np.allclose(r["rew"], r_on[t], rtol=1e-9, atol=1e-9), (i, t)
+                s_o = o.get_state()
+                for k in ("rob", "rhist", "ball"):
+                    assert np.allclose(s_on[k], s_o[k], rtol=1e-9, atol=1e-9), (i, k)
+    finally:
+        emul.use_libm_sincos(False)
+        oracle.scratch_mode(0)
+    print(f"{preset}: {n} scenarios x {K} fused steps: {int(tot[0])} frames replayed ({int(tot[1])} as whole frames), "
+          f"{int(tot[2])} robot-robot phases replayed")
+    assert tot[1] > 1000 and (preset == "TRAIN" or tot[2] > 500)
+
+
+def test_memos_are_exact_on_long_random_rollouts(oracle):
+    """Random-action rollouts from the product's own resets (no hand-built contact): 48 GAME envs x 240 steps in
+    fused chunks of 24, memo on vs off, bit for bit."""
+    from emul.emul import EmulEnv
+    from roborugby_b200 import _lib
+    rng = np.random.default_rng(9)
+    tot = np.zeros(3)
+    for i in range(48):
+        on = EmulEnv(_cfg("GAME", 0), 4, 8, 5)
+        off = EmulEnv(_cfg("GAME", _lib.FLAG_NO_SQUEEZE_MEMO), 4, 8, 5)
+        on.reset(100 + i, 0, construct=True)
+        off.set_state(on.get_state())
+        for chunk in range(10):
+            a = rng.integers(0, 8, (24, 4))
+            if chunk % 3 == 2:
+                a[:, :] = a[:1, :]      # a held action: robots keep driving into whatever they hit
+            e_on, r_on, cnt = on.step_k(a)
+            e_off, r_off, _ = off.step_k(a)
+            tot += cnt
+            assert e_on == e_off and np.array_equal(r_on, r_off), (i, chunk)
+            s_on, s_off = on.get_state(), off.get_state()
+            for k in s_on:
+                assert np.array_equal(s_on[k], s_off[k]), (i, chunk, k)
+            if e_on:
+                break
+    print(f"random rollouts: {int(tot[0])} frames replayed ({int(tot[1])} whole), {int(tot[2])} robot-robot phases replayed")
+    assert tot[2] > 0
 
 
 @pytest.mark.parametrize("preset", ["GAME", "TRAIN"])
