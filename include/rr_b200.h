@@ -65,6 +65,8 @@ extern "C" {
 #define RR_OBS_LIDAR6_V2 2   /* SingleBall_6wayLidar_v2 :287-406 (11)  */
 #define RR_OBS_ALLCOORDS 3   /* AllCoords :47-83 (3R+2B)               */
 #define RR_OBS_ALLCOORDS_PRIOR 4 /* AllCoords_WithPrior :86-110 (6R+4B): + rectDblPriorStep of every robot and ball */
+#define RR_OBS_LIDAR6_V1 5   /* SingleBall_6wayLidar :168-284 (11): the first 6-way lidar, which main.py:42-49 composes
+                                "so Stephen can play" */
 
 /* per-env error bits == the Python exceptions of the path */
 #define RR_ERR_STEP_AFTER_DONE 1u   /* RR_EnvBase.py:261-262 */
@@ -151,6 +153,19 @@ int rr_get_starting_positions(rr_sim *s, double *rob3, double *ball2);
 
 /* get_game_state(int_team=HAPPY / GRUMPY) of the current state (RR_Observers.py). */
 int rr_observe(rr_sim *s, void *obs_h_dev, void *obs_g_dev, void *stream);
+
+/* get_game_state(obj_robot=lstRobots[robot], obj_ball=lstBalls[ball]) of the current state for every env
+ * (RR_Observers.py:133-136 PosBall_BasicLidar, which ignores the ball; :187-203 SingleBall_6wayLidar; :304-320
+ * SingleBall_6wayLidar_v2): obs_dev = out_t [N][D], from the robot's own team's point of view.  ball < 0 selects the
+ * default lstPosBalls[0].  ball_dev (int32 [N], device, may be NULL) overrides `ball` with one index per env; a
+ * negative entry yields a NaN row (a "Stephen" player without a ball).  RR_E_INVALID for the AllCoords observers
+ * ("Robot-specific state output not supported.", :59-60). */
+int rr_observe_entity(rr_sim *s, int32_t robot, int32_t ball, const int32_t *ball_dev, void *obs_dev, void *stream);
+
+/* Stephen.__ponder (DQN_pytorch_player.py:39-61) for every env: the greedy nearest-ball assignment of the players that
+ * drive robots_host[0..n_robots): balls inside either goal's triangle are ignored, each player gets at most one ball
+ * and each ball one player, closest pairs first.  assign_dev = int32 [N][n_robots]: ball index or -1. */
+int rr_assign_balls(rr_sim *s, const int32_t *robots_host, int32_t n_robots, int32_t *assign_dev, void *stream);
 
 /* step() x k_steps in ONE fused kernel launch; device buffers (layouts above).  Any output
  * pointer may be NULL.  n_actions = values supplied per env per step (robots beyond it keep

@@ -107,7 +107,7 @@ def _put_state(out, i, t, st):
 def _obs_dim(env_id, R, B):
     return {"RoboRugby-v0": 0, "RoboRugbySimple-v0": 5, "RoboRugbySimpleDuel-v2": 5,
             "RoboRugbySimpleDuel-v3": 11, "DuelAllCoords": 3 * R + 2 * B, "DuelAllMixins": 5, "DuelCutChain": 5,
-            "DuelAllCoordsPrior": 6 * R + 4 * B}[env_id]
+            "DuelAllCoordsPrior": 6 * R + 4 * B, "DuelLidar6v1": 11}[env_id]
 
 
 # ------------------------------------------------------------------ state builders for `inject`
@@ -509,6 +509,70 @@ def task_reset_fixed(args):
     return args, out
 
 
+def task_entity(args):
+    """Per-robot / per-ball observations and the "Stephen" ball assignment along chase rollouts:
+    ent[i, t, r, b] = get_game_state(obj_robot=lstRobots[r], obj_ball=lstBalls[b]) after step t (RR_Observers.py:133-136,
+    :187-203, :304-320), asg[i, t] = Stephen.__ponder's assignment for the players of `hive` (DQN_pytorch_player.py:39-61)."""
+    preset, env_id, seed, n, T, hive = args
+    import ref_harness as H
+    const = H.load_reference(preset)
+    env = H.make_env(env_id)
+    u = env.unwrapped
+    R, B = len(u.lstRobots), len(u.lstBalls)
+    D = _obs_dim(env_id, R, B)
+    out = _empty(n, T, R, B, R, D)
+    out["ent"] = np.full((n, T, R, B, D), np.nan)
+    out["asg"] = np.full((n, T, len(hive)), -2, np.int32)
+    out["hive"] = np.asarray(hive, np.int32)
+    S, players = H.stephen_hive(env, hive)
+    rng = random.Random(seed)
+    signal.signal(signal.SIGALRM, _alarm)
+    i = attempt = 0
+    while i < n:
+        random.seed(seed * 1000 + attempt)
+        attempt += 1
+        signal.alarm(30 + 3 * T)
+        try:
+            env.reset()
+            st = H.extract(env)
+            H.inject(env, st)
+            _put_state(out, i, 0, st)
+            ok = True
+            for t in range(T):
+                acts = [_chase_action(u, k, rng) for k in range(R)]
+                out["act"][i, t, :R] = acts
+                st, oh, og, rew, done, ng, exc = _step_record(H, env, list(acts), D)
+                if exc:
+                    ok = False
+                    break
+                _put_state(out, i, t + 1, st)
+                out["obs_h"][i, t], out["obs_g"][i, t] = oh, og
+                out["rew"][i, t], out["done"][i, t], out["naughty"][i, t] = rew, done, ng
+                for r in range(R):
+                    for b in range(B):
+                        out["ent"][i, t, r, b] = np.asarray(u.get_game_state(obj_robot=u.lstRobots[r], obj_ball=u.lstBalls[b]), np.float64)
+                out["asg"][i, t] = H.stephen_assignments(env, S, players)
+            if ok:
+                i += 1
+        except _Timeout:
+            print(f"timeout in {args}, attempt {attempt}", flush=True)
+        finally:
+            signal.alarm(0)
+    return args, out
+
+
+def main_entity():
+    """robot-/ball-specific observations of the three lidar observers and the Stephen assignment."""
+    jobs = [("GAME", "RoboRugbySimpleDuel-v2", 91, 2, 40, (0, 1)), ("GAME", "RoboRugbySimpleDuel-v3", 92, 3, 48, (0, 1, 2, 3)),
+            ("GAME", "DuelLidar6v1", 93, 3, 48, (0, 1))]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(processes=3, maxtasksperchild=1) as pool:
+        res = [pool.apply_async(task_entity, (a,)) for a in jobs]
+        for r in res:
+            args, out = r.get()
+            _save(f"{args[0]}_{args[1]}_entity_s{args[2]}", out)
+
+
 def main_extra():
     """Later additions, generated without touching the files of main(): observer O4 (AllCoords)."""
     jobs = [(task_rollout, ("GAME", "DuelAllCoords", "chase", 51, 2, 48)),
@@ -582,5 +646,7 @@ if __name__ == "__main__":
         main_extra()
     elif len(sys.argv) > 1 and sys.argv[1] == "mixins":
         main_mixins()
+    elif len(sys.argv) > 1 and sys.argv[1] == "entity":
+        main_entity()
     else:
         main()

@@ -123,6 +123,19 @@ def make_env(env_id, through_gym=False):
         env = DuelAllCoords()
         env.spec = gym.spec("RoboRugbySimpleDuel-v2")
         return env
+    if env_id == "DuelLidar6v1":
+        # SimpleDuel2's reward mixins with the first 6-way lidar observer (RR_Observers.py:168-284), the one main.py:42-49
+        # composes "so Stephen can play"
+        import robo_rugby.gym_env.RR_ScoreKeepers as sk
+        import robo_rugby.gym_env.RR_Observers as obs
+        import robo_rugby.gym_env.RR_EnvBase as base
+
+        class DuelLidar6v1(sk.PushPosBallsToGoal, sk.ChasePosBall, sk.NaughtyBots, obs.SingleBall_6wayLidar, base.GameEnv_Simple):
+            pass
+
+        env = DuelLidar6v1()
+        env.spec = gym.spec("RoboRugbySimpleDuel-v2")
+        return env
     if env_id in MIXIN_COMPOSITIONS:
         # ad-hoc reward-mixin compositions (class-definition order) on SimpleDuel2's observer and action space
         import robo_rugby.gym_env.RR_ScoreKeepers as sk
@@ -138,6 +151,32 @@ def make_env(env_id, through_gym=False):
     env = getattr(importlib.import_module(mod), cls)()
     env.spec = gym.spec(env_id)
     return env
+
+
+def stephen_hive(env, robot_indices):
+    """The reference's "Stephen" players (DQN_pytorch_player.py) for the given robots WITHOUT their pickled network
+    (absent from the tree): the objects are created without __init__ (which would load the pickle and insist on the
+    v1 lidar observer) and registered in the class-level hive, so that the reference's own greedy nearest-ball
+    assignment, Stephen.__ponder (:39-61), can be called.  Returns (Stephen class, [player per robot index])."""
+    import DQN_pytorch_player as dp
+    S = dp.Stephen
+    S._Stephen__hive = set()
+    S._Stephen__env = env.unwrapped
+    players = []
+    for i in robot_indices:
+        p = S.__new__(S)
+        p.env, p.robot = env.unwrapped, env.unwrapped.lstRobots[i]
+        S._Stephen__hive.add(p)
+        players.append(p)
+    return S, players
+
+
+def stephen_assignments(env, S, players):
+    """Run Stephen.__ponder and return the assigned ball index per player (-1 = none)."""
+    S._Stephen__ponder()
+    asg = S._Stephen__assignments
+    balls = env.unwrapped.lstBalls
+    return [balls.index(asg[p]) if p in asg else -1 for p in players]
 
 
 def reset_scratch():

@@ -49,6 +49,7 @@ extern "C" {
 #define RRO_OBS_LIDAR6_V2 2   /* SingleBall_6wayLidar_v2 :287-406, 11 values */
 #define RRO_OBS_ALLCOORDS 3   /* AllCoords               :47-83, 3R+2B values */
 #define RRO_OBS_ALLCOORDS_PRIOR 4 /* AllCoords_WithPrior :86-110, 6R+4B values */
+#define RRO_OBS_LIDAR6_V1 5   /* SingleBall_6wayLidar    :168-284, 11 values (what main.py composes for the "Stephen" player) */
 
 /* error bits: the Python exceptions of the path */
 #define RRO_ERR_STEP_AFTER_DONE 1u      /* RR_EnvBase.py:261-262 */
@@ -98,6 +99,13 @@ uint32_t rro_step(rro_env *e, const double *actions, int n_actions, double *obs_
 
 /* Observation of the current state (get_game_state(int_team=...)); team = +1 happy, -1 grumpy. */
 uint32_t rro_observe(rro_env *e, int team, double *obs);
+/* get_game_state(obj_robot=lstRobots[robot], obj_ball=lstBalls[ball]); ball < 0 = default ball.  Returns the error mask,
+ * or 0xffffffff when the observer does not support robot-specific output (AllCoords raises NotImplementedError). */
+uint32_t rro_observe_entity(rro_env *e, int robot, int ball, double *obs);
+/* The "Stephen" players' greedy nearest-ball assignment (DQN_pytorch_player.py:39-61): balls inside either goal's
+ * triangle are ignored; (player, ball) pairs by ascending distance, each player one ball, each ball one player.
+ * assign[i] = ball index of robots[i], or -1 (the player then returns thrust (0, 0), :68-69). */
+void rro_assign_balls(rro_env *e, const int *robots, int n, int *assign);
 
 /* reset(bln_randomize_pos) fed from an explicit stream of randint() results (RR_EnvBase.py:155-216).
  * Returns the number of draws consumed, or -1 if the stream ran out. */

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "librr_oracle.so")
 
 REW_CHASE, REW_PUSHPOS, REW_NAUGHTY = 1, 2, 4
-OBS_NONE, OBS_BASIC_LIDAR, OBS_LIDAR6_V2, OBS_ALLCOORDS = 0, 1, 2, 3
+OBS_NONE, OBS_BASIC_LIDAR, OBS_LIDAR6_V2, OBS_ALLCOORDS, OBS_ALLCOORDS_PRIOR, OBS_LIDAR6_V1 = 0, 1, 2, 3, 4, 5
 
 ERR_BITS = {
     1: "STEP_AFTER_DONE", 2: "TOO_MANY_COMMANDS", 4: "BOT_COLLISIONS", 8: "UNDO_FAILED",
@@ -63,6 +63,9 @@ def lib():
         L.rro_step.restype = C.c_uint32
         L.rro_observe.argtypes = [C.c_void_p, C.c_int, dp]
         L.rro_observe.restype = C.c_uint32
+        L.rro_observe_entity.argtypes = [C.c_void_p, C.c_int, C.c_int, dp]
+        L.rro_observe_entity.restype = C.c_uint32
+        L.rro_assign_balls.argtypes = [C.c_void_p, ip, C.c_int, ip]
         L.rro_reset_draws.argtypes = [C.c_void_p, C.c_int, ip, C.c_int]
         L.rro_reset_draws.restype = C.c_int
         L.rro_reset_philox.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_uint32]
@@ -137,6 +140,21 @@ class OracleEnv:
         o = np.full(max(self.obs_dim, 1), np.nan)
         lib().rro_observe(self._h, int(team), _dp(o))
         return o[:self.obs_dim]
+
+    def observe_entity(self, robot, ball=-1):
+        """get_game_state(obj_robot=lstRobots[robot], obj_ball=lstBalls[ball]); ball=-1 is the default ball."""
+        o = np.full(max(self.obs_dim, 1), np.nan)
+        err = lib().rro_observe_entity(self._h, int(robot), int(ball), _dp(o))
+        if err == 0xffffffff:
+            raise NotImplementedError("Robot-specific state output not supported.")
+        return o[:self.obs_dim]
+
+    def assign_balls(self, robots):
+        """Stephen.__ponder: greedy nearest-ball assignment for the players driving `robots`; -1 = no ball."""
+        r = np.ascontiguousarray(robots, np.int32)
+        out = np.zeros(len(r), np.int32)
+        lib().rro_assign_balls(self._h, _ip(r), len(r), _ip(out))
+        return out
 
     def reset_draws(self, draws, randomize=True):
         d = np.ascontiguousarray(draws, np.int32)

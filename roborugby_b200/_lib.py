@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("RR_B200_LIB", os.path.join(_HERE, "librr_b200.so"))
 ABI_VERSION = 2
 PRESET_GAME, PRESET_TRAIN = 0, 1
 REW_CHASE, REW_PUSHPOS, REW_NAUGHTY = 1, 2, 4
-OBS_NONE, OBS_BASIC_LIDAR, OBS_LIDAR6_V2, OBS_ALLCOORDS = 0, 1, 2, 3
+OBS_NONE, OBS_BASIC_LIDAR, OBS_LIDAR6_V2, OBS_ALLCOORDS, OBS_ALLCOORDS_PRIOR, OBS_LIDAR6_V1 = 0, 1, 2, 3, 4, 5
 NUM_STATS = 8
 STAT_NAMES = ("episodes", "return_happy", "return_grumpy", "length", "naughty", "errors", "steps", "squeeze_replays")
 FLAG_NO_SQUEEZE_MEMO = 1
@@ -59,6 +59,8 @@ SIGNATURES = {
     "rr_set_starting_positions": (C.c_int, [_vp, _vp, _vp]),
     "rr_get_starting_positions": (C.c_int, [_vp, _vp, _vp]),
     "rr_observe": (C.c_int, [_vp, _vp, _vp, _vp]),
+    "rr_observe_entity": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
+    "rr_assign_balls": (C.c_int, [_vp, _vp, _i32, _vp, _vp]),
     "rr_step": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "rr_step_host": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "rr_set_state": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),

@@ -424,6 +424,52 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_observe(const __grid_consta
   }
 }
 
+// get_game_state(obj_robot=..., obj_ball=...) for one robot index and a ball index that is the same for every env
+// (ball_dev == nullptr) or differs per env (ball_dev[i]; a negative entry gives a NaN row: "no ball assigned")
+template <class L, typename OutT>
+__global__ void __launch_bounds__(L::kMaxBlock, 1) k_observe_entity(const __grid_constant__ Consts k, const double *sf,
+                                                              const int32_t *si, int64_t N, int robot, int ball,
+                                                              const int32_t *ball_dev, void *obs) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const double *trig_tab = stage_trig_table();
+  if (i >= N) return;
+  typename L::E e;
+  double cold[L::E::kColdDoubles];
+  e.trig = trig_tab;
+  load_env<L>(e, cold, k, sf, si, N, i);
+  const int dim = obs_dim_of<typename L::E>(k.observer);
+  double ob[kMaxObs];
+  unsigned oerr = 0;
+  const int b = ball_dev ? ball_dev[i] : ball;
+  if (ball_dev && b < 0) {
+    for (int q = 0; q < dim; q++) ob[q] = rr_nan();
+  } else {
+    observe_entity(e, k, robot, b, ob, oerr);
+  }
+  for (int q = 0; q < dim; q++) ((OutT *)obs)[i * dim + q] = (OutT)ob[q];
+}
+
+struct RobotList { int n; int idx[8]; };
+
+// Stephen.__ponder for every env: assign[i][j] = ball of the player driving robots.idx[j], or -1
+template <class L>
+__global__ void __launch_bounds__(L::kMaxBlock, 1) k_assign_balls(const __grid_constant__ Consts k, const double *sf,
+                                                            const int32_t *si, int64_t N, const RobotList robots,
+                                                            int32_t *assign) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const double *trig_tab = stage_trig_table();
+  if (i >= N) return;
+  typename L::E e;
+  double cold[L::E::kColdDoubles];
+  e.trig = trig_tab;
+  load_env<L>(e, cold, k, sf, si, N, i);
+  int rb[8], out[8];
+  for (int j = 0; j < robots.n; j++) rb[j] = robots.idx[j];
+  unsigned err = 0;
+  assign_balls(e, k, rb, robots.n, out, err);
+  for (int j = 0; j < robots.n; j++) assign[i * robots.n + j] = out[j];
+}
+
 }  // namespace rr
 
 // =============================================================================================
@@ -523,6 +569,7 @@ static cudaError_t opt_in_shared_memory() {
   };
   set(k_step<L, float>); set(k_step<L, double>); set(k_init<L>); set(k_reset<L>); set(k_reset_fixed<L>);
   set(k_observe<L, float>); set(k_observe<L, double>);
+  set(k_observe_entity<L, float>); set(k_observe_entity<L, double>); set(k_assign_balls<L>);
   return e;
 }
 
@@ -551,7 +598,7 @@ int rr_create(const rr_config *cfg, int64_t n_envs, int device, rr_sim **out) {
   if (!cfg || !out || n_envs <= 0) return fail(RR_E_INVALID, "bad arguments");
   if (cfg->abi_version != RR_ABI_VERSION) return fail(RR_E_INVALID, "abi_version mismatch");
   if (cfg->preset != RR_PRESET_GAME && cfg->preset != RR_PRESET_TRAIN) return fail(RR_E_INVALID, "unknown preset");
-  if (cfg->observer < 0 || cfg->observer > RR_OBS_ALLCOORDS_PRIOR) return fail(RR_E_INVALID, "unknown observer");
+  if (cfg->observer < 0 || cfg->observer > RR_OBS_LIDAR6_V1) return fail(RR_E_INVALID, "unknown observer");
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if (ce != cudaSuccess || ndev == 0)
@@ -617,6 +664,7 @@ int rr_obs_dim(const rr_sim *s) {
   switch (s->cfg.observer) {
     case RR_OBS_BASIC_LIDAR: return 5;
     case RR_OBS_LIDAR6_V2: return 11;
+    case RR_OBS_LIDAR6_V1: return 11;
     case RR_OBS_ALLCOORDS: return 3 * s->R + 2 * s->B;
     case RR_OBS_ALLCOORDS_PRIOR: return 6 * s->R + 4 * s->B;
     default: return 0;
@@ -753,6 +801,42 @@ int rr_observe(rr_sim *s, void *obs_h, void *obs_g, void *stream) {
     LAUNCH_PRESET(s, st, (k_observe<L, double>), s->k, s->sf, s->si, s->N, obs_h, obs_g);
   else
     LAUNCH_PRESET(s, st, (k_observe<L, float>), s->k, s->sf, s->si, s->N, obs_h, obs_g);
+  s->launches++;
+  CK(cudaGetLastError());
+  return RR_OK;
+}
+
+int rr_observe_entity(rr_sim *s, int32_t robot, int32_t ball, const int32_t *ball_dev, void *obs, void *stream) {
+  if (!s || !obs) return fail(RR_E_INVALID, "null argument");
+  const int ob = s->cfg.observer;
+  if (ob == RR_OBS_ALLCOORDS || ob == RR_OBS_ALLCOORDS_PRIOR)
+    return fail(RR_E_INVALID, "Robot-specific state output not supported.");  // RR_Observers.py:59-60
+  if (ob == RR_OBS_NONE) return fail(RR_E_INVALID, "this env has no observer");
+  if (robot < 0 || robot >= s->R) return fail(RR_E_INVALID, "robot index out of range");
+  if (!ball_dev && ball >= s->B) return fail(RR_E_INVALID, "ball index out of range");
+  ON_DEVICE(s->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (s->cfg.out_f64)
+    LAUNCH_PRESET(s, st, (k_observe_entity<L, double>), s->k, s->sf, s->si, s->N, (int)robot, (int)ball, ball_dev, obs);
+  else
+    LAUNCH_PRESET(s, st, (k_observe_entity<L, float>), s->k, s->sf, s->si, s->N, (int)robot, (int)ball, ball_dev, obs);
+  s->launches++;
+  CK(cudaGetLastError());
+  return RR_OK;
+}
+
+int rr_assign_balls(rr_sim *s, const int32_t *robots_host, int32_t n_robots, int32_t *assign_dev, void *stream) {
+  if (!s || !robots_host || !assign_dev) return fail(RR_E_INVALID, "null argument");
+  if (n_robots < 1 || n_robots > s->R || n_robots > 8) return fail(RR_E_INVALID, "n_robots out of range");
+  RobotList rl{};
+  rl.n = n_robots;
+  for (int j = 0; j < n_robots; j++) {
+    if (robots_host[j] < 0 || robots_host[j] >= s->R) return fail(RR_E_INVALID, "robot index out of range");
+    rl.idx[j] = robots_host[j];
+  }
+  ON_DEVICE(s->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  LAUNCH_PRESET(s, st, (k_assign_balls<L>), s->k, s->sf, s->si, s->N, rl, assign_dev);
   s->launches++;
   CK(cudaGetLastError());
   return RR_OK;

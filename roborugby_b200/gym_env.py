@@ -75,6 +75,61 @@ class _GoalView:
         return False
 
 
+class _RectView:
+    """The read-only part of a sprite's FloatRect that scripts look at (MyUtils.py:114-354)."""
+
+    def __init__(self, cx, cy, left, right, top, bottom, rotation=0.0):
+        self.centerx, self.centery, self.left, self.right, self.top, self.bottom = cx, cy, left, right, top, bottom
+        self.rotation = rotation
+
+    @property
+    def center(self):
+        return (self.centerx, self.centery)
+
+
+class RobotView:
+    """lstRobots[i] (RR_Robot.py): identity (index, team) plus a snapshot of the pose taken when it is read."""
+
+    def __init__(self, env, index, team):
+        self._env, self.index, self.intTeam = env, index, team
+
+    @property
+    def rectDbl(self):
+        r = self._env.get_state()["rob"][self.index]
+        return _RectView(*r[:6], rotation=r[6])
+
+    @property
+    def dblRotation(self):
+        return float(self._env.get_state()["rob"][self.index][6])
+
+    @property
+    def lngLThrust(self):
+        return int(self._env.get_state()["rflag"][self.index][0])
+
+    @property
+    def lngRThrust(self):
+        return int(self._env.get_state()["rflag"][self.index][1])
+
+
+class BallView:
+    """lstBalls[i] (RR_Ball.py): positive balls first (RR_EnvBase.py:62-68, :101-109)."""
+
+    def __init__(self, env, index, positive):
+        self._env, self.index, self.is_positive, self.is_negative = env, index, positive, not positive
+
+    @property
+    def rectDbl(self):
+        return _RectView(*self._env.get_state()["ball"][self.index][:6])
+
+    @property
+    def dbl_velocity_x(self):
+        return float(self._env.get_state()["ball"][self.index][6])
+
+    @property
+    def dbl_velocity_y(self):
+        return float(self._env.get_state()["ball"][self.index][7])
+
+
 # GameEnv_Simple._dct_thrust_from_direction (RR_EnvBase.py:593-602)
 _THRUST = {0: (1, 1), 1: (-1, -1), 2: (-1, 1), 3: (1, -1), 4: (0, 1), 5: (1, 0), 6: (-1, 0), 7: (0, -1)}
 
@@ -108,6 +163,10 @@ class RoboRugbyEnv:
         hi = max(self.preset.arena_width, self.preset.arena_height, 360)  # RR_Observers.py:30-37
         self.observation_space = Box(-hi, hi, shape=(self._v.obs_dim,), dtype=np.float32) if self._v.obs_dim else None
         self.sprHappyGoal, self.sprGrumpyGoal = _GoalView(), _GoalView()
+        # entity lists the reference's scripts index into (main.py:59-63, RR_EnvBase.py:54-68)
+        nh, npos = self.preset.num_robots_happy, self.preset.num_ball_pos
+        self.lstRobots = [RobotView(self, i, TEAM_HAPPY if i < nh else TEAM_GRUMPY) for i in range(R)]
+        self.lstBalls = [BallView(self, i, i < npos) for i in range(self._v.num_balls)]
         self._reward = {TEAM_HAPPY: 0.0, TEAM_GRUMPY: 0.0}
         self._elapsed = 0
         self.np_random = None
@@ -163,7 +222,10 @@ class RoboRugbyEnv:
         info = DebugInfo(self._np_obs(obs_g), rew[1])
         if self.time_limit and self._elapsed >= self.spec.max_episode_steps:
             info["TimeLimit.truncated"] = not self.game_is_done()
-        return self._np_obs(obs_h), rew[0], d, info
+        # GameEnv.step returns self.get_game_state() (no team, RR_EnvBase.py:296): None for PosBall_BasicLidar, the
+        # happy team's observation for the others
+        obs = None if self._v.cfg.observer == _lib.OBS_BASIC_LIDAR else self._np_obs(obs_h)
+        return obs, rew[0], d, info
 
     # -- introspection used by the training scripts --------------------------------------------
     def _np_obs(self, t):
@@ -172,19 +234,55 @@ class RoboRugbyEnv:
         a = t[0, 0].cpu().numpy().astype(np.float64)
         return None if np.isnan(a).all() else a
 
+    @property
+    def lstHappyBots(self):
+        return self.lstRobots[:self.preset.num_robots_happy]
+
+    @property
+    def lstGrumpyBots(self):
+        return self.lstRobots[self.preset.num_robots_happy:]
+
+    @property
+    def lstPosBalls(self):
+        return self.lstBalls[:self.preset.num_ball_pos]
+
+    @property
+    def lstNegBalls(self):
+        return self.lstBalls[self.preset.num_ball_pos:]
+
+    def _entity_obs(self, robot, ball):
+        a = self._v.observe_entity(robot.index, None if ball is None else ball.index)[0].cpu().numpy().astype(np.float64)
+        return None if np.isnan(a).all() else a
+
     def get_game_state(self, int_team=None, obj_robot=None, obj_ball=None):
-        """get_game_state(int_team=...) (RR_Observers.py); per-robot / per-ball views are not exposed."""
-        if obj_robot is not None or obj_ball is not None:
-            raise NotImplementedError("robot-/ball-specific observations are a next-row item (SURVEY.md §8f)")
-        if self._v.obs_dim == 0:
+        """get_game_state(int_team, obj_robot, obj_ball) with every observer's own rules (RR_Observers.py:50-60,
+        :133-141, :187-203, :304-320).  obj_robot / obj_ball are entries of lstRobots / lstBalls."""
+        ob = self._v.cfg.observer
+        if ob == _lib.OBS_NONE:
             return None
+        if ob in (_lib.OBS_ALLCOORDS, _lib.OBS_ALLCOORDS_PRIOR):
+            if int_team is None:
+                int_team = TEAM_HAPPY
+            if obj_robot:
+                raise NotImplementedError("Robot-specific state output not supported.")  # :59-60
+        elif ob == _lib.OBS_BASIC_LIDAR:
+            if obj_robot:
+                return self._entity_obs(obj_robot, None)  # :134-135 (obj_ball is ignored: lstPosBalls[0])
+            if int_team not in (TEAM_HAPPY, TEAM_GRUMPY):
+                return None  # :140-141
+        else:  # the two 6-way lidar observers, :187-203 / :304-320
+            if int_team is not None and obj_robot is not None:
+                assert obj_robot.intTeam == int_team
+            if obj_robot is not None or obj_ball is not None:
+                if obj_robot is None:
+                    bots = self.lstHappyBots if int_team in (None, TEAM_HAPPY) else self.lstGrumpyBots
+                    if not bots:
+                        return None
+                    obj_robot = bots[0]
+                return self._entity_obs(obj_robot, obj_ball)
+            if int_team is None:
+                int_team = TEAM_HAPPY
         oh, og = self._v.observe()
-        if int_team is None:
-            # PosBall_BasicLidar returns None without a team (RR_Observers.py:133-141); the other
-            # observers default to the happy team (:58-59, :313-315)
-            if self._v.cfg.observer == _lib.OBS_BASIC_LIDAR:
-                return None
-            int_team = TEAM_HAPPY
         t = oh if int_team == TEAM_HAPPY else og
         a = t[0].cpu().numpy().astype(np.float64)
         return None if np.isnan(a).all() else a

@@ -19,3 +19,28 @@ def og_twitchy_actions(shape, device="cuda:0", generator=None):
     a = torch.where(u <= 0.5, torch.full_like(a, _FORWARD), a)
     a = torch.where(u <= 0.05, torch.full_like(a, _LEFT), a)
     return a
+
+
+# GameEnv_Simple._dct_thrust_from_direction (RR_EnvBase.py:593-602) as a tensor table: action id -> (left, right)
+_THRUST_TABLE = ((1, 1), (-1, -1), (-1, 1), (1, -1), (0, 1), (1, 0), (-1, 0), (0, -1))
+
+
+def stephen_thrusts(env, robots, choose_action, epsilon=0.2):
+    """The "Stephen" players (DQN_pytorch_player.py:9-92) for a whole batch, on the device.
+
+    env: RoboRugbyVecEnv with one of the 6-way lidar observers; robots: the robot indices the players drive;
+    choose_action(obs [N, D], epsilon_override=...) -> action ids [N] (e.g. VecDQNAgent.choose_actions: the reference
+    loads a pickled DQNAgent that is not part of its tree, so the network is the caller's).
+    Per step, as Stephen.__consult does (:63-72): one greedy nearest-ball assignment for all players
+    (rr_assign_balls), each player's observation of ITS robot and ITS ball (rr_observe_entity), an eps-greedy action
+    (epsilon_override=0.2), translated to a thrust pair; a player without a ball returns (0, 0).
+    Returns float32 thrusts [N, len(robots), 2] and the assignment int32 [N, len(robots)]."""
+    asg = env.assign_balls(robots)
+    table = torch.tensor(_THRUST_TABLE, dtype=torch.float32, device=env.device)
+    out = torch.zeros(env.num_envs, len(robots), 2, dtype=torch.float32, device=env.device)
+    for j, r in enumerate(robots):
+        has = asg[:, j] >= 0
+        obs = torch.nan_to_num(env.observe_entity(r, asg[:, j]).float(), nan=0.0)
+        act = choose_action(obs, epsilon_override=epsilon).long()
+        out[:, j] = torch.where(has.unsqueeze(1), table[act], torch.zeros_like(table[act]))
+    return out, asg

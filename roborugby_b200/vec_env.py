@@ -156,6 +156,29 @@ class RoboRugbyVecEnv:
             _lib.check(self.lib.rr_observe(self._h, b["obs_h"].data_ptr(), b["obs_g"].data_ptr(), self._stream()))
         return b["obs_h"][0, :, :self.obs_dim], b["obs_g"][0, :, :self.obs_dim]
 
+    def observe_entity(self, robot, ball=None):
+        """get_game_state(obj_robot=lstRobots[robot], obj_ball=lstBalls[ball]) for every env -> [N, D] (a fresh tensor).
+        ball: None (the observer's default ball), an index, or an int32 tensor [N] with one index per env (negative:
+        a NaN row).  RR_Observers.py:133-136, :187-203, :304-320."""
+        out = torch.empty(self.num_envs, max(self.obs_dim, 1), dtype=self.out_dtype, device=self.device)
+        bdev, bidx = None, -1
+        if torch.is_tensor(ball):
+            ball = ball.to(self.device, torch.int32).contiguous()
+            assert ball.shape == (self.num_envs,)
+            bdev = ball.data_ptr()
+        elif ball is not None:
+            bidx = int(ball)
+        _lib.check(self.lib.rr_observe_entity(self._h, int(robot), bidx, bdev, out.data_ptr(), self._stream()))
+        return out[:, :self.obs_dim]
+
+    def assign_balls(self, robots):
+        """The "Stephen" players' greedy nearest-ball assignment (DQN_pytorch_player.py:39-61) for the players driving
+        `robots`, in every env -> int32 [N, len(robots)] on the device: ball index, or -1."""
+        r = np.ascontiguousarray(robots, np.int32)
+        out = torch.empty(self.num_envs, len(r), dtype=torch.int32, device=self.device)
+        _lib.check(self.lib.rr_assign_balls(self._h, r.ctypes.data_as(C.c_void_p), len(r), out.data_ptr(), self._stream()))
+        return out
+
     def step(self, actions):
         """One env-step for all envs.  actions: uint8 [N, A] (discrete ids) or float32 [N, A]."""
         obs_h, obs_g, rew, done = self.step_k(actions, 1)

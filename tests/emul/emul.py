@@ -50,6 +50,10 @@ def lib():
         L.emul_sincos2.restype = None
         L.emul_predicates.argtypes = [C.POINTER(Config), vp, vp, vp, vp, vp, vp, vp]
         L.emul_predicates.restype = None
+        L.emul_observe_entity.argtypes = [C.POINTER(Config), vp, vp, vp, vp, vp, C.c_int, C.c_int, vp]
+        L.emul_observe_entity.restype = C.c_uint
+        L.emul_assign_balls.argtypes = [C.POINTER(Config), vp, vp, vp, vp, vp, vp, C.c_int, vp]
+        L.emul_assign_balls.restype = None
         L.emul_step_k.argtypes = [C.POINTER(Config), vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]
         L.emul_step_k.restype = C.c_uint
         L.emul_last_replays.argtypes = []
@@ -116,6 +120,24 @@ class EmulEnv:
         lib().emul_observe(C.byref(self.cfg), _p(self.rob), _p(self.rhist), _p(self.rflag), _p(self.ball),
                            _p(self.stepc), int(team), _p(o))
         return o[:self.obs_dim]
+
+
+def observe_entity(cfg, st, robot, ball, obs_dim):
+    rob = np.ascontiguousarray(st["rob"], np.float64); rhist = np.ascontiguousarray(st["rhist"], np.float64)
+    rflag = np.ascontiguousarray(st["rflag"], np.int32); bl = np.ascontiguousarray(st["ball"], np.float64)
+    step = np.zeros(1, np.int32)
+    o = np.full(max(obs_dim, 1), np.nan)
+    lib().emul_observe_entity(C.byref(cfg), _p(rob), _p(rhist), _p(rflag), _p(bl), _p(step), int(robot), int(ball), _p(o))
+    return o[:obs_dim]
+
+
+def assign_balls(cfg, st, robots):
+    rob = np.ascontiguousarray(st["rob"], np.float64); rhist = np.ascontiguousarray(st["rhist"], np.float64)
+    rflag = np.ascontiguousarray(st["rflag"], np.int32); bl = np.ascontiguousarray(st["ball"], np.float64)
+    step = np.zeros(1, np.int32)
+    r = np.ascontiguousarray(robots, np.int32); out = np.zeros(len(r), np.int32)
+    lib().emul_assign_balls(C.byref(cfg), _p(rob), _p(rhist), _p(rflag), _p(bl), _p(step), _p(r), len(r), _p(out))
+    return out
 
 
 def predicates(cfg, st):

@@ -189,6 +189,33 @@ unsigned emul_observe(const rr_config *cfg, double *rob, double *rhist, int32_t 
   return err;
 }
 
+// get_game_state(obj_robot=..., obj_ball=...) and the Stephen assignment through the device source
+unsigned emul_observe_entity(const rr_config *cfg, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,
+                             int robot, int ball_idx, double *obs) {
+  Consts k = make_consts(*cfg);
+  unsigned err = 0;
+  if (cfg->preset == RR_PRESET_GAME) {
+    HostEnv<2, 2, 4, 4> h; load(h.e, k, rob, rhist, rflag, ball, *step); observe_entity(h.e, k, robot, ball_idx, obs, err);
+  } else {
+    HostEnv<1, 0, 1, 0> h; load(h.e, k, rob, rhist, rflag, ball, *step); observe_entity(h.e, k, robot, ball_idx, obs, err);
+  }
+  return err;
+}
+
+void emul_assign_balls(const rr_config *cfg, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,
+                       const int32_t *robots, int n, int32_t *assign) {
+  Consts k = make_consts(*cfg);
+  unsigned err = 0;
+  int rb[8], out[8];
+  for (int j = 0; j < n; j++) rb[j] = robots[j];
+  if (cfg->preset == RR_PRESET_GAME) {
+    HostEnv<2, 2, 4, 4> h; load(h.e, k, rob, rhist, rflag, ball, *step); assign_balls(h.e, k, rb, n, out, err);
+  } else {
+    HostEnv<1, 0, 1, 0> h; load(h.e, k, rob, rhist, rflag, ball, *step); assign_balls(h.e, k, rb, n, out, err);
+  }
+  for (int j = 0; j < n; j++) assign[j] = out[j];
+}
+
 // For every (robot, robot) and (ball, robot) pair of a GAME state: bit0 = the cheap rejection fired,
 // bit1 = the reference predicate is True.  A pair with both bits set would be a parity bug.
 void emul_predicates(const rr_config *cfg, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,

@@ -9,15 +9,17 @@ STATE_KEYS = ("rob", "rhist", "rflag", "ball", "step")
 
 def parse_name(path):
     """GAME_RoboRugbySimpleDuel-v2_chase_s2.npz -> (preset, env_id, kind)."""
-    m = re.match(r"(GAME|TRAIN)_(RoboRugby[A-Za-z]*-v\d|DuelAllCoordsPrior|DuelAllCoords|DuelAllMixins|DuelCutChain)_([a-z]+)", os.path.basename(path))
+    m = re.match(r"(GAME|TRAIN)_(RoboRugby[A-Za-z]*-v\d|DuelAllCoordsPrior|DuelAllCoords|DuelAllMixins|DuelCutChain|DuelLidar6v1)_([a-z]+)", os.path.basename(path))
     return m.group(1), m.group(2), m.group(3)
 
 
 # Ad-hoc class compositions (not registered ids) used by some golden files: base id + observer override.
 OBS_ALLCOORDS = 3
 OBS_ALLCOORDS_PRIOR = 4
+OBS_LIDAR6_V1 = 5
 CUSTOM = {"DuelAllCoords": ("RoboRugbySimpleDuel-v2", OBS_ALLCOORDS),
-          "DuelAllCoordsPrior": ("RoboRugbySimpleDuel-v2", OBS_ALLCOORDS_PRIOR)}
+          "DuelAllCoordsPrior": ("RoboRugbySimpleDuel-v2", OBS_ALLCOORDS_PRIOR),
+          "DuelLidar6v1": ("RoboRugbySimpleDuel-v2", OBS_LIDAR6_V1)}
 # ... and reward-mixin compositions, in class-definition order (oracle/ref_harness.py builds exactly these classes)
 CUSTOM_MIXINS = {
     "DuelAllMixins": ("RoboRugbySimpleDuel-v2", ["KeepMovingGuys", "DontDriveInGoals", "BaseDestruction", "PushNegBallsFromGoal",

@@ -215,3 +215,34 @@ def test_kernel_source_fixed_layout_reset(path, trig):
             else:
                 assert np.allclose(got[k], want[k], rtol=0, atol=1e-11), (i, k)
         assert np.allclose(env.observe(1), d["obs_h"][i, 0], rtol=1e-9, atol=1e-9, equal_nan=True)
+
+
+ENTITY = golden_files("*_entity_*.npz")
+
+
+@pytest.mark.parametrize("path", ENTITY, ids=[p.split("/")[-1] for p in ENTITY])
+def test_kernel_source_entity_observations_and_assignment(path):
+    """observe_entity / assign_balls of rr_sim.cuh (get_game_state(obj_robot, obj_ball), Stephen.__ponder) on the host
+    against what the reference returned after every step of a chase rollout: assignments exact, observations within
+    the 1e-9 bar (atan / sqrt last bits), most of them bit-identical."""
+    from emul import emul
+    d, cfg, env, preset, env_id = _make(path)
+    n, T, R, B, D = d["ent"].shape
+    emul.use_libm_sincos(True)
+    try:
+        exact = total = 0
+        for i in range(n):
+            for t in range(0, T, 3):
+                st = state_at(d, i, t + 1)
+                for r in range(R):
+                    for b in range(B):
+                        got = emul.observe_entity(cfg, st, r, b, D)
+                        want = d["ent"][i, t, r, b]
+                        assert np.allclose(got, want, rtol=1e-9, atol=1e-9), (i, t, r, b, got, want)
+                        exact += np.array_equal(got, want)
+                        total += 1
+                assert np.array_equal(emul.assign_balls(cfg, st, d["hive"]), d["asg"][i, t]), (i, t)
+    finally:
+        emul.use_libm_sincos(False)
+    print(f"{path.split('/')[-1]}: {exact}/{total} entity observations bit-identical")
+    assert exact >= 0.9 * total

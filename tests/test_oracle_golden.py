@@ -11,7 +11,7 @@ import pytest
 from conftest import golden_files
 from golden_util import actions_at, apply_overrides, parse_name, resolve_env, state_at, state_diff, states_equal
 
-ROLLOUTS = [f for f in golden_files("*.npz") if parse_name(f)[2] in ("random", "chase", "sticky", "inject", "partial")]
+ROLLOUTS = [f for f in golden_files("*.npz") if parse_name(f)[2] in ("random", "chase", "sticky", "inject", "partial", "entity")]
 
 
 def _eq(a, b):
@@ -108,3 +108,35 @@ def test_oracle_fixed_layout_reset_matches_reference(oracle, path):
         got, want = env.get_state(), state_at(d, i, 1)
         assert states_equal(got, want), (i, state_diff(got, want))
         assert _eq(env.observe(1), d["obs_h"][i, 0]) and _eq(env.observe(-1), d["obs_g"][i, 0])
+
+
+ENTITY = golden_files("*_entity_*.npz")
+
+
+@pytest.mark.parametrize("path", ENTITY, ids=[p.split("/")[-1] for p in ENTITY])
+def test_oracle_entity_observations_and_stephen_assignment(oracle, path):
+    """get_game_state(obj_robot=..., obj_ball=...) of every robot and ball (RR_Observers.py:133-136, :187-203, :304-320)
+    and the "Stephen" players' greedy nearest-ball assignment (DQN_pytorch_player.py:39-61), both recorded from the
+    reference after every step of a chase rollout: bit for bit."""
+    preset, env_id, _ = parse_name(path)
+    d = np.load(path)
+    n, T, R, B = d["ent"].shape[:4]
+    base_id, observer = resolve_env(env_id)
+    cfg = apply_overrides(oracle.default_config(preset, base_id), env_id)
+    env = oracle.OracleEnv(cfg=cfg)
+    hive = d["hive"]
+    assigned = 0
+    for i in range(n):
+        for t in range(T):
+            env.set_state(state_at(d, i, t + 1))
+            for r in range(R):
+                for b in range(B):
+                    assert _eq(env.observe_entity(r, b), d["ent"][i, t, r, b]), (i, t, r, b)
+                assert _eq(env.observe_entity(r, -1), d["ent"][i, t, r, 0]), "default ball = lstPosBalls[0]"
+            got = env.assign_balls(hive)
+            assert np.array_equal(got, d["asg"][i, t]), (i, t, got, d["asg"][i, t])
+            assigned += int((got >= 0).sum())
+    assert assigned > 0
+    if env.cfg.observer in (3, 4):
+        with pytest.raises(NotImplementedError):
+            env.observe_entity(0, 0)

@@ -285,8 +285,13 @@ def test_gpu_gym_wrapper_drop_in():
     obs = env.unwrapped.get_game_state(int_team=rr.TEAM_HAPPY)
     assert obs.shape == (5,) and env.unwrapped.get_game_state(int_team=rr.TEAM_GRUMPY) is None
     o, r, d, info = env.step([0])
-    assert o.shape == (5,) and isinstance(r, float) and d is False
-    assert info.adblGrumpyState is None and info.dblGrumpyScore == pytest.approx(-r + 0.0, abs=1e9)
+    # GameEnv.step returns get_game_state() without a team (RR_EnvBase.py:296): None for this observer, like reset()
+    assert o is None and isinstance(r, float) and d is False
+    assert env.unwrapped.get_game_state(int_team=rr.TEAM_HAPPY).shape == (5,)
+    assert env.unwrapped.get_game_state(obj_robot=env.unwrapped.lstHappyBots[0]).shape == (5,)
+    assert info.adblGrumpyState is None and isinstance(info.dblGrumpyScore, float)   # TRAIN preset: no grumpy robot
+    assert len(env.lstRobots) == 1 and len(env.lstBalls) == 1 and env.lstPosBalls[0].is_positive and not env.lstNegBalls
+    assert env.lstRobots[0].rectDbl.center == tuple(env.get_state()["rob"][0][:2])
     with pytest.raises(Exception, match="commands but only 1 robots"):
         env.step([0, 1])
     assert env.sprHappyGoal.get_score() == 0 and not env.sprGrumpyGoal.is_destroyed()
@@ -623,3 +628,68 @@ def test_gpu_squeeze_memo_replay_is_exact(oracle, preset):
         oracle.scratch_mode(0)
     print(f"{preset}: ~{pinned:.0f} pinned-ball frames in {N} envs x {K} steps, {st_on['squeeze_replays']:.0f} replayed by the memo")
     assert st_on["squeeze_replays"] > 0.4 * pinned > 0
+
+
+ENTITY = golden_files("*_entity_*.npz")
+
+
+@pytest.mark.parametrize("path", ENTITY, ids=[p.split("/")[-1] for p in ENTITY])
+def test_gpu_entity_observations_and_stephen_assignment(path):
+    """rr_observe_entity / rr_assign_balls (get_game_state(obj_robot=..., obj_ball=...) of robots 0-3 and balls 0-7,
+    RR_Observers.py:133-136, :187-203, :304-320; Stephen.__ponder, DQN_pytorch_player.py:39-61) against what the
+    reference returned after every step of a chase rollout: every record in its own env, one launch per (robot, ball)."""
+    preset, env_id, _ = parse_name(path)
+    d = np.load(path)
+    n, T, R, B, D = d["ent"].shape
+    flat = {k: d[k][:, 1:].reshape((n * T,) + d[k].shape[2:]) for k in STATE_KEYS}
+    env = _venv(env_id, n * T, preset)
+    env.set_state(flat)
+    want = d["ent"].reshape(n * T, R, B, D)
+    exact = total = 0
+    for r in range(R):
+        for b in range(B):
+            got = env.observe_entity(r, b).cpu().numpy()
+            assert np.allclose(got, want[:, r, b], rtol=1e-9, atol=1e-9), (r, b)
+            exact += int((got == want[:, r, b]).all(1).sum()); total += n * T
+        assert np.array_equal(env.observe_entity(r).cpu().numpy(), env.observe_entity(r, 0).cpu().numpy())
+    hive = [int(x) for x in d["hive"]]
+    asg = env.assign_balls(hive)
+    assert np.array_equal(asg.cpu().numpy(), d["asg"].reshape(n * T, len(hive)))
+    # per-env ball indices: every player looks at ITS ball; players without a ball get a NaN row
+    for j, r in enumerate(hive):
+        got = env.observe_entity(r, asg[:, j]).cpu().numpy()
+        a = asg[:, j].cpu().numpy()
+        for i in np.nonzero(a >= 0)[0][:64]:
+            assert np.allclose(got[i], want[i, r, a[i]], rtol=1e-9, atol=1e-9)
+        assert np.isnan(got[a < 0]).all()
+    print(f"{path.split('/')[-1]}: {exact}/{total} entity observations bit-identical, assignments exact")
+    env.close()
+
+
+def test_gpu_stephen_players_drive_the_full_game():
+    """main.py:42-63 batched: the full game's env (continuous thrust pairs) with a 6-way lidar observer, two "Stephen"
+    players on the happy robots (their network is the caller's: a freshly initialised VecDQNAgent), OG_Twitchy on the
+    grumpy ones.  Checks the plumbing: thrust pairs follow the assignment, unassigned players stand still, the env
+    steps, and the single-env wrapper offers the same calls with the reference's signatures."""
+    from roborugby_b200.dqn import VecDQNAgent
+    from roborugby_b200.players import og_twitchy_actions, stephen_thrusts, _THRUST_TABLE
+    from roborugby_b200.vec_env import RoboRugbyVecEnv
+    import roborugby_b200 as rr
+    N = 256
+    env = RoboRugbyVecEnv("RoboRugby-v0", N, preset="GAME", device="cuda:0", seed=4, observer=5)   # SingleBall_6wayLidar
+    assert env.obs_dim == 11 and not env.discrete
+    agent = VecDQNAgent(11, device="cuda:0", seed=2)
+    table = torch.tensor(_THRUST_TABLE, dtype=torch.float32, device="cuda:0")
+    for it in range(5):
+        thr, asg = stephen_thrusts(env, [0, 1], agent.choose_actions)
+        assert thr.shape == (N, 2, 2) and (asg >= 0).all() and (asg[:, 0] != asg[:, 1]).all()
+        twitchy = table[og_twitchy_actions((N, 2), device="cuda:0").long()]
+        acts = torch.cat([thr, twitchy], 1).reshape(N, 8)
+        env.step(acts)
+    st = env.get_state()
+    assert (st["rflag"][:, :, :2] != 0).any() and (env.error_mask() == 0).all()
+    one = rr.RoboRugbyEnv("RoboRugby-v0", preset="GAME", observer=5)
+    o = one.get_game_state(obj_robot=one.lstHappyBots[1], obj_ball=one.lstNegBalls[2])
+    assert o.shape == (11,) and one.get_game_state().shape == (11,)
+    with pytest.raises(AssertionError):
+        one.get_game_state(int_team=rr.TEAM_GRUMPY, obj_robot=one.lstHappyBots[0])
