@@ -116,7 +116,12 @@ typedef struct rr_config {
   uint64_t seed;        /* Philox key */
   int64_t env_offset;   /* global index of this handle's env 0 (rank * n_envs when sharded) */
   uint32_t flags;       /* RR_FLAG_* */
-  int32_t goal_scoring; /* reserved (0) */
+  int32_t goal_scoring; /* 0: the reference's HEAD, where goal scoring is dead code (scores 0, goals never destroyed,
+                           balls never removed: SURVEY.md §0.4); 1: goal scoring as intended, i.e. RR_Goal.py:54-91 and
+                           the commit block of GameEnv.__old_step (RR_EnvBase.py:461-511) made live: a ball that stays
+                           150 steps inside a goal's triangle scores +-500 (added to the scorekeepers' step rewards), is
+                           removed from play; three negative balls destroy a goal; done also when a goal is destroyed
+                           or no ball is left (:555-559); BaseDestruction pays out */
 } rr_config;
 
 typedef struct rr_sim rr_sim;
@@ -169,15 +174,22 @@ int rr_assign_balls(rr_sim *s, const int32_t *robots_host, int32_t n_robots, int
 
 /* step() x k_steps in ONE fused kernel launch; device buffers (layouts above).  Any output
  * pointer may be NULL.  n_actions = values supplied per env per step (robots beyond it keep
- * their thrust, RR_EnvBase.py:272-273). */
+ * their thrust, RR_EnvBase.py:272-273).  A discrete action id above 7 (KeyError in the reference, :603-606) leaves the
+ * env untouched for that step and raises RR_ERR_BAD_ACTION (done = 1).
+ * Alignment: none required.  Result rows are written as coalesced 128-bit stores when a buffer is 16-byte aligned and
+ * its per-step row (N * D * sizeof(out_t), N * 2 * sizeof(out_t), N bytes) is a multiple of 16 bytes, element by
+ * element otherwise; discrete actions with n_actions == 4 are read with one 32-bit load per env when the buffer is
+ * 4-byte aligned, byte by byte otherwise. */
 int rr_step(rr_sim *s, const void *actions_dev, int32_t n_actions, int32_t k_steps, void *obs_h_dev,
             void *obs_g_dev, void *rew_dev, uint8_t *done_dev, void *stream);
 
-/* Same call with HOST buffers: copies actions host->device, launches, copies results back and
- * synchronises the stream before returning.  This is what a single-process caller of the
- * reference's env.step() would bind.  Where the copies dominate (TRAIN preset) the k steps run as
- * up to four launches whose result rows travel while the next launch computes; results are
- * identical to one launch.  Pinned host buffers are needed for the copies to be asynchronous. */
+/* Same call with HOST buffers: copies actions host->device, launches, and synchronises the stream before returning.
+ * This is what a single-process caller of the reference's env.step() would bind.  When every result buffer is pinned
+ * (page-locked, e.g. cudaHostAlloc / torch pin_memory) the kernel writes its rows straight into host memory (zero
+ * copy: the device-to-host traffic overlaps the launch and nothing is staged in HBM).  Pageable buffers are staged in
+ * HBM and copied; where those copies dominate (TRAIN preset) the k steps then run as up to four launches whose rows
+ * travel while the next launch computes.  Results are identical on every path.  RR_HOST_ZEROCOPY=0 / RR_HOST_CHUNKS=n
+ * in the environment at rr_create force the staged path / the number of launches. */
 int rr_step_host(rr_sim *s, const void *actions_host, int32_t n_actions, int32_t k_steps,
                  void *obs_h_host, void *obs_g_host, void *rew_host, uint8_t *done_host, void *stream);
 
@@ -185,10 +197,19 @@ int rr_step_host(rr_sim *s, const void *actions_host, int32_t n_actions, int32_t
  * (oracle/ref_harness.py): rob[N][R][7] = cx,cy,left,right,top,bottom,rot (FloatRect fields,
  * MyUtils.py:122-130); rhist[N][R][3] = pose in history slot count-1 (RR_Robot.py:43-58);
  * rflag[N][R][3] = thrust_l, thrust_r, hist_valid; ball[N][B][8] = cx,cy,l,r,t,b,vx,vy;
- * step[N] = lngStepCount.  These synchronise the device. */
+ * step[N] = lngStepCount.  These synchronise the device.  rr_set_state also sets what is derived from the injected
+ * pose: rectDblPriorStep of every robot and ball (observer RR_OBS_ALLCOORDS_PRIOR) becomes a copy() of the injected
+ * rects, as the reference's on_reset / on_step_begin leave it; goal bookkeeping (goal_scoring) restarts as after a
+ * reset.  rr_get_state does not return the prior-step poses (they are visible through rr_observe). */
 int rr_set_state(rr_sim *s, const double *rob, const double *rhist, const int32_t *rflag,
                  const double *ball, const int32_t *step);
 int rr_get_state(rr_sim *s, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step);
+
+/* Goal bookkeeping (goal_scoring = 1) to HOST; any pointer may be NULL.  alive[N]: bit b = ball b still in play;
+ * score[N][2]: Goal.get_score() of the happy and the grumpy goal (RR_Goal.py:87-88); destroyed[N]: bit 0 happy goal,
+ * bit 1 grumpy goal (Goal.is_destroyed, :90-91); dwell[N][2][B]: steps ball b has stayed inside that goal's triangle
+ * (0 = not tracked).  Synchronises the device. */
+int rr_goal_state(rr_sim *s, int32_t *alive_host, int32_t *score_host, int32_t *destroyed_host, int32_t *dwell_host);
 
 /* Per-env sticky error mask (RR_ERR_*) to HOST; clear != 0 zeroes it afterwards. */
 int rr_error_mask(rr_sim *s, uint32_t *err_host, int32_t clear);

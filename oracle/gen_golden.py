@@ -107,7 +107,7 @@ def _put_state(out, i, t, st):
 def _obs_dim(env_id, R, B):
     return {"RoboRugby-v0": 0, "RoboRugbySimple-v0": 5, "RoboRugbySimpleDuel-v2": 5,
             "RoboRugbySimpleDuel-v3": 11, "DuelAllCoords": 3 * R + 2 * B, "DuelAllMixins": 5, "DuelCutChain": 5,
-            "DuelAllCoordsPrior": 6 * R + 4 * B, "DuelLidar6v1": 11}[env_id]
+            "DuelAllCoordsPrior": 6 * R + 4 * B, "DuelLidar6v1": 11, "DuelGoals": 5}[env_id]
 
 
 # ------------------------------------------------------------------ state builders for `inject`
@@ -561,6 +561,117 @@ def task_entity(args):
     return args, out
 
 
+def task_goals(args):
+    """Goal scoring "as intended" (ref_harness._GOAL_SCORING_PATCHES): trajectories of T steps from states with balls
+    parked inside the goal triangles; records the usual step outputs (the reward includes the +-500 score delta) plus,
+    after every step: alive[B], score[2] (happy goal, grumpy goal get_score()), destroyed[2], dwell[2][B] (steps the ball
+    has been in that goal so far, 0 = not tracked)."""
+    preset, env_id, seed, n, T = args
+    import ref_harness as H
+    const = H.load_reference(preset, goal_scoring=True)
+    env = H.make_env(env_id)
+    u = env.unwrapped
+    R, B = len(u.lstRobots), len(u.lstBalls)
+    D = _obs_dim(env_id, R, B)
+    W, Hh = const.ARENA_WIDTH, const.ARENA_HEIGHT
+    continuous = env_id == "RoboRugby-v0"
+    thrust = {0: (1, 1), 1: (-1, -1), 2: (-1, 1), 3: (1, -1), 4: (0, 1), 5: (1, 0), 6: (-1, 0), 7: (0, -1)}
+    out = _empty(n, T, R, B, 2 * R if continuous else R, D)
+    out["alive"] = np.zeros((n, T + 1, B), np.int32)
+    out["score"] = np.zeros((n, T + 1, 2), np.int32)
+    out["destroyed"] = np.zeros((n, T + 1, 2), np.int32)
+    out["dwell"] = np.zeros((n, T + 1, 2, B), np.int32)
+    out["delta"] = np.zeros((n, T), np.int32)
+    rng = random.Random(seed)
+    signal.signal(signal.SIGALRM, _alarm)
+
+    def goal_record(i, t):
+        out["alive"][i, t] = [int(b.alive()) for b in u.lstBalls]
+        for gi, g in enumerate((u.sprHappyGoal, u.sprGrumpyGoal)):
+            out["score"][i, t, gi] = g.get_score()
+            out["destroyed"][i, t, gi] = int(g.is_destroyed())
+            for bi, b in enumerate(u.lstBalls):
+                out["dwell"][i, t, gi, bi] = (g.lngFrameCount - g.dctBallsPrior[b] + 1) if b in g.dctBallsPrior else 0
+
+    i = attempt = 0
+    while i < n:
+        random.seed(seed * 1000 + attempt)
+        attempt += 1
+        signal.alarm(60 + 3 * T)
+        try:
+            env.reset()
+            # park some balls (at rest) inside the goal triangles: happy = bottom right, grumpy = top left
+            kind = i % 4
+            spots_h = [(W - 40 - 35 * k, Hh - 40 - 30 * (k % 2)) for k in range(5)]
+            spots_g = [(40 + 35 * k, 40 + 30 * (k % 2)) for k in range(5)]
+            neg0 = const.NUM_BALL_POS
+            if kind == 0:    # three negative balls + one positive in the happy goal: it is destroyed
+                plan = [(neg0 + k, spots_h[k]) for k in range(min(3, const.NUM_BALL_NEG))] + [(0, spots_h[3])]
+            elif kind == 1:  # one of each in the grumpy goal, one positive in the happy goal
+                plan = [(0, spots_g[0]), (neg0, spots_g[1]), (1 % const.NUM_BALL_POS, spots_h[0])] if const.NUM_BALL_NEG else [(0, spots_g[0])]
+            elif kind == 2:  # three negatives in the grumpy goal
+                plan = [(neg0 + k, spots_g[k]) for k in range(min(3, const.NUM_BALL_NEG))] if const.NUM_BALL_NEG else [(0, spots_h[0])]
+            else:            # every ball in some goal: the game ends when none is left
+                plan = [(b, (spots_h if b % 2 else spots_g)[b // 2]) for b in range(B)]
+            for b, (x, y) in plan:
+                u.lstBalls[b].rectDbl.center = (float(x), float(y))
+            for ri, rb in enumerate(u.lstRobots):   # the robots start in the middle of the arena, clear of every parked ball
+                rb.rectDbl.center = (W / 2 - 90.0 + 60.0 * ri, Hh / 2 - 60.0 + 45.0 * ri)
+            for bi, bl in enumerate(u.lstBalls):    # and the balls that are not parked keep away from them
+                if bi not in [b for b, _ in plan]:
+                    bl.rectDbl.center = (80.0 + 70.0 * bi, Hh - 90.0 - 40.0 * (bi % 3)) if bi % 2 else (W - 80.0 - 70.0 * bi, 90.0 + 40.0 * (bi % 3))
+            st = H.extract(env)
+            H.inject(env, st)
+            _put_state(out, i, 0, st)
+            goal_record(i, 0)
+            ok = True
+            # kinds 0, 2: robot 0 spins on the spot (GameEnv_Simple.step needs at least one command: np.concatenate of an
+            # empty list raises), the others stand still; kinds 1, 3: chasing robots, which push balls out of the goals
+            driven = 1 if kind in (0, 2) else (R if kind == 1 else 1)
+            for t in range(T):
+                if u.game_is_done():
+                    out["exc"][i, t:] = 2   # marks "episode over": no further steps recorded
+                    for tt in range(t, T):
+                        _put_state(out, i, tt + 1, H.extract(env)); goal_record(i, tt + 1)
+                    break
+                acts = [2] if kind in (0, 2) else [_chase_action(u, k, rng) for k in range(driven)]
+                if continuous:   # GameEnv.step takes (left, right) thrust pairs
+                    call = [tuple(float(v) for v in thrust[a]) for a in acts]
+                    out["act"][i, t, :2 * driven] = [v for pr in call for v in pr]
+                else:
+                    call = list(acts)
+                    out["act"][i, t, :driven] = acts
+                stt, oh, og, rew, done, ng, exc = _step_record(H, env, call, D)
+                if exc:
+                    ok = False
+                    break
+                _put_state(out, i, t + 1, stt)
+                out["obs_h"][i, t], out["obs_g"][i, t] = oh, og
+                out["rew"][i, t], out["done"][i, t], out["naughty"][i, t] = rew, done, ng
+                out["delta"][i, t] = u.dblGoalScoreDelta
+                goal_record(i, t + 1)
+            if ok:
+                i += 1
+        except _Timeout:
+            print(f"timeout in {args}, attempt {attempt}", flush=True)
+        finally:
+            signal.alarm(0)
+    return args, out
+
+
+def main_goals():
+    """goal scoring as intended, from the in-memory patched reference."""
+    # (SimpleDuel-v2 has NaughtyBots: its cut on_step_end chain keeps the goals from ever scoring, a negative case)
+    jobs = [("GAME", "DuelGoals", 101, 8, 165), ("GAME", "RoboRugby-v0", 102, 4, 165),
+            ("GAME", "RoboRugbySimpleDuel-v2", 103, 2, 160), ("TRAIN", "DuelGoals", 104, 4, 165)]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(processes=4, maxtasksperchild=1) as pool:
+        res = [pool.apply_async(task_goals, (a,)) for a in jobs]
+        for r in res:
+            args, out = r.get()
+            _save(f"{args[0]}_{args[1]}_goals_s{args[2]}", out)
+
+
 def main_entity():
     """robot-/ball-specific observations of the three lidar observers and the Stephen assignment."""
     jobs = [("GAME", "RoboRugbySimpleDuel-v2", 91, 2, 40, (0, 1)), ("GAME", "RoboRugbySimpleDuel-v3", 92, 3, 48, (0, 1, 2, 3)),
@@ -648,5 +759,7 @@ if __name__ == "__main__":
         main_mixins()
     elif len(sys.argv) > 1 and sys.argv[1] == "entity":
         main_entity()
+    elif len(sys.argv) > 1 and sys.argv[1] == "goals":
+        main_goals()
     else:
         main()

@@ -41,8 +41,58 @@ ENV_IDS = {
 }
 
 
-def load_reference(preset):
-    """Import the reference with preset 'GAME' (as shipped) or 'TRAIN' (GAME_MODE=False)."""
+# In-memory source patches that switch on the reference's goal scoring "as intended" (SURVEY.md §8f rank 3).  At the
+# reference's HEAD Goal.track_balls / update_score are only reached from GameEnv.__old_step (RR_EnvBase.py:458-520), whose
+# commit block is commented out, so scores, goal destruction and ball removal are dead code.  The patches below make
+# exactly that code live and repair what stops it from running; nothing else of the reference changes:
+#   P1 RR_Goal.py:80      `sprBall.is_positive()` -> `sprBall.is_positive` (it is a property: the call raises TypeError)
+#   P2 RR_EnvBase.py:294  before on_step_end(): the two track_balls calls (:463-464) and the commit block (:497-511,
+#                         uncommented): balls that stayed TIME_BALL_IN_GOAL_STEPS in a goal are scored and killed; the
+#                         score delta (`dblHappyScore = dblScoreDelta; dblGrumpyScore = -dblScoreDelta`, :510-511) is
+#                         added to the scorekeepers' step rewards before their own on_step_end terms
+#   P3 kill() also stops the ball (velocity and force 0): _roll_balls iterates lstBalls, dead balls included (:341-343),
+#                         and a dead ball never gets on_frame_begin again, so without this it would coast on a stale force
+#   P4 RR_EnvBase.py:204-207 reset() re-adds dead balls in lstBalls order (Group is insertion-ordered: a revived ball
+#                         would otherwise move to the end of every pair enumeration)
+_GOAL_SCORING_PATCHES = {
+    "robo_rugby.gym_env.RR_Goal": [
+        (b"                if sprBall.is_positive():", b"                if sprBall.is_positive:"),
+    ],
+    "robo_rugby.gym_env.RR_EnvBase": [
+        (b"            self.on_frame_end()\n\n        self.on_step_end()\n",
+         b"            self.on_frame_end()\n\n"
+         b"        self.sprHappyGoal.track_balls(self.grpBalls.sprites())\n"
+         b"        self.sprGrumpyGoal.track_balls(self.grpBalls.sprites())\n"
+         b"        dblScoreDelta = 0\n"
+         b"        for sprBall in self.sprHappyGoal.update_score():\n"
+         b"            dblScoreDelta += const.POINTS_BALL_SCORED if sprBall.tplColor == const.COLOR_BALL_POS else -const.POINTS_BALL_SCORED\n"
+         b"            sprBall.kill()\n"
+         b"            sprBall.dbl_velocity_x = sprBall.dbl_velocity_y = 0\n"
+         b"            sprBall.dbl_force_x = sprBall.dbl_force_y = 0\n"
+         b"        for sprBall in self.sprGrumpyGoal.update_score():\n"
+         b"            dblScoreDelta += -const.POINTS_BALL_SCORED if sprBall.tplColor == const.COLOR_BALL_POS else const.POINTS_BALL_SCORED\n"
+         b"            sprBall.kill()\n"
+         b"            sprBall.dbl_velocity_x = sprBall.dbl_velocity_y = 0\n"
+         b"            sprBall.dbl_force_x = sprBall.dbl_force_y = 0\n"
+         b"        self.dblGoalScoreDelta = dblScoreDelta\n"
+         b"        if hasattr(self, 'reward_happy'):\n"
+         b"            self.reward_happy += dblScoreDelta\n"
+         b"            self.reward_grumpy -= dblScoreDelta\n\n"
+         b"        self.on_step_end()\n"),
+        (b"        for spr_ball in self.lstBalls:\n            if not spr_ball.alive():\n"
+         b"                self.grpBalls.add(spr_ball)\n                self.grpAllSprites.add(spr_ball)\n",
+         b"        if not all(b.alive() for b in self.lstBalls):\n"
+         b"            for spr_ball in self.lstBalls:\n                spr_ball.kill()\n"
+         b"            for spr_ball in self.lstBalls:\n"
+         b"                self.grpBalls.add(spr_ball)\n                self.grpAllSprites.add(spr_ball)\n"),
+    ],
+}
+
+
+def load_reference(preset, goal_scoring=False):
+    """Import the reference with preset 'GAME' (as shipped) or 'TRAIN' (GAME_MODE=False); goal_scoring=True also
+    applies _GOAL_SCORING_PATCHES.  All patches are applied to the module SOURCE IN MEMORY as it is read from the
+    read-only tree; no reference file is copied or written."""
     assert preset in ("GAME", "TRAIN")
     if "robo_rugby" in sys.modules:
         raise RuntimeError("reference already imported in this process; constants bind at import")
@@ -51,25 +101,32 @@ def load_reference(preset):
     for p in (REF_ROOT, _SHIMS):
         if p not in sys.path:
             sys.path.insert(0, p)
+    patches = {}
     if preset == "TRAIN":
-        name = "robo_rugby.gym_env.RR_Constants"
-        path = os.path.join(REF_ROOT, "robo_rugby", "gym_env", "RR_Constants.py")
+        patches["robo_rugby.gym_env.RR_Constants"] = [(b"GAME_MODE = True", b"GAME_MODE = False")]
+    if goal_scoring:
+        patches.update(_GOAL_SCORING_PATCHES)
+    if patches:
+        paths = {name: os.path.join(REF_ROOT, *name.split(".")) + ".py" for name in patches}
 
         class _Loader(importlib.machinery.SourceFileLoader):
             def get_data(self, p):
                 data = super().get_data(p)
-                if p == path:
-                    assert data.count(b"GAME_MODE = True") == 1
-                    data = data.replace(b"GAME_MODE = True", b"GAME_MODE = False")
+                for name, path in paths.items():
+                    if p == path:
+                        data = data.replace(b"\r\n", b"\n")
+                        for old, new in patches[name]:
+                            assert data.count(old) == 1, (name, old)
+                            data = data.replace(old, new)
                 return data
 
-            def get_code(self, fullname):  # never use or write a .pyc for the patched module
-                return self.source_to_code(self.get_data(path), path)
+            def get_code(self, fullname):  # never use or write a .pyc for a patched module
+                return self.source_to_code(self.get_data(paths[fullname]), paths[fullname])
 
         class _Finder(importlib.abc.MetaPathFinder):
             def find_spec(self, fullname, p=None, target=None):
-                if fullname == name:
-                    return importlib.util.spec_from_file_location(name, path, loader=_Loader(name, path))
+                if fullname in paths:
+                    return importlib.util.spec_from_file_location(fullname, paths[fullname], loader=_Loader(fullname, paths[fullname]))
                 return None
 
         sys.meta_path.insert(0, _Finder())
@@ -84,6 +141,9 @@ MIXIN_COMPOSITIONS = {
     "DuelAllMixins": ["KeepMovingGuys", "DontDriveInGoals", "BaseDestruction", "PushNegBallsFromGoal",
                       "PushPosBallsToGoal", "ChasePosBall", "NaughtyBots"],
     "DuelCutChain": ["DontDriveInGoals", "ChasePosBall", "NaughtyBots", "KeepMovingGuys"],
+    # no NaughtyBots: its on_step_end does not call super(), which also cuts GameEnv.on_step_end and with it the goals'
+    # own on_step_end (RR_Goal.py:58-64), without which no ball ever scores
+    "DuelGoals": ["BaseDestruction", "PushPosBallsToGoal", "ChasePosBall"],
 }
 
 

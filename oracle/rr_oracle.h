@@ -74,6 +74,9 @@ typedef struct {
   uint32_t reward_order;     /* RRO_MIX_* sequence in which the on_step_end bodies execute: reverse MRO order, cut at
                                 NaughtyBots, whose on_step_end does not call super() (RR_ScoreKeepers.py:130-135);
                                 0 = Naughty, Chase, PushPos, PushNeg, BaseDestruction, DontDrive, KeepMoving */
+  int goal_scoring;          /* 1: goal scoring as intended (RR_Goal.py:54-91 + RR_EnvBase.py:461-511 made live; the
+                                reference side is oracle/ref_harness.py _GOAL_SCORING_PATCHES); 0: the reference's HEAD,
+                                where that code is dead and scores / destruction are constants. */
 } rro_config;
 
 typedef struct rro_env rro_env;
@@ -127,6 +130,11 @@ void rro_scratch_reset(void);
 
 void rro_set_starting_positions(rro_env *e, const double *rob3, const double *ball2);
 long rro_rollout(rro_env *e, long n_steps, uint64_t seed);
+
+/* Goal bookkeeping of the current state (goal_scoring): alive[B]; score[2] = get_score() of the happy and the grumpy
+ * goal; destroyed[2]; dwell[2][B] (steps the ball has stayed in that goal, 0 = not tracked); delta = score change
+ * committed by the last step (+ = good for happy). */
+void rro_goal_state(const rro_env *e, int32_t *alive, int32_t *score, int32_t *destroyed, int32_t *dwell, int32_t *delta);
 
 /* Test instrumentation: number of physics frames since the last clear in which all ten resolve passes failed and the
  * undo loop ran (RR_EnvBase.py:284-287): the "ball pinned between a robot and a wall" frames. */

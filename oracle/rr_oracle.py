@@ -29,6 +29,7 @@ class Config(C.Structure):
         ("game_length_steps", C.c_int), ("game_mode", C.c_int),
         ("reward_mask", C.c_uint32), ("observer", C.c_int),
         ("discrete", C.c_int), ("time_limit", C.c_int), ("reward_order", C.c_uint32),
+        ("goal_scoring", C.c_int),
     ]
 
 
@@ -73,6 +74,7 @@ def lib():
         L.rro_set_starting_positions.argtypes = [C.c_void_p, dp, dp]
         L.rro_rollout.argtypes = [C.c_void_p, C.c_long, C.c_uint64]
         L.rro_rollout.restype = C.c_long
+        L.rro_goal_state.argtypes = [C.c_void_p, ip, ip, ip, ip, ip]
         L.rro_debug_failed_frames.argtypes = [C.c_int]
         L.rro_debug_failed_frames.restype = C.c_long
         L.rro_scratch_mode.argtypes = [C.c_int]
@@ -140,6 +142,13 @@ class OracleEnv:
         o = np.full(max(self.obs_dim, 1), np.nan)
         lib().rro_observe(self._h, int(team), _dp(o))
         return o[:self.obs_dim]
+
+    def goal_state(self):
+        """alive[B], score[2] (happy goal, grumpy goal), destroyed[2], dwell[2, B], delta of the last step."""
+        alive = np.zeros(self.B, np.int32); score = np.zeros(2, np.int32); destroyed = np.zeros(2, np.int32)
+        dwell = np.zeros((2, self.B), np.int32); delta = np.zeros(1, np.int32)
+        lib().rro_goal_state(self._h, _ip(alive), _ip(score), _ip(destroyed), _ip(dwell), _ip(delta))
+        return dict(alive=alive, score=score, destroyed=destroyed, dwell=dwell, delta=int(delta[0]))
 
     def observe_entity(self, robot, ball=-1):
         """get_game_state(obj_robot=lstRobots[robot], obj_ball=lstBalls[ball]); ball=-1 is the default ball."""

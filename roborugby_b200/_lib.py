@@ -65,6 +65,7 @@ SIGNATURES = {
     "rr_step_host": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "rr_set_state": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "rr_get_state": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "rr_goal_state": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "rr_error_mask": (C.c_int, [_vp, _vp, _i32]),
     "rr_last_naughty": (C.c_int, [_vp, _vp]),
     "rr_get_stats": (C.c_int, [_vp, _vp]),

@@ -120,6 +120,11 @@ __device__ __forceinline__ void load_env(typename L::E &e, double *cold, const C
   e.step = si[(L::R + 0) * N + i];
   e.episode = (unsigned)si[(L::R + 1) * N + i];
   e.err = (unsigned)si[(L::R + 2) * N + i];
+  e.goal_clear();
+  if (k.goal_scoring) {  // goal bookkeeping: alive mask, scored masks, dwell counters [2][B] (extra int32 columns)
+#pragma unroll 1
+    for (int q = 0; q < L::E::kGoalDoubles; q++) e.gs(q) = (double)(unsigned)si[(L::R + 4 + q) * N + i];
+  }
 }
 
 template <class L>
@@ -155,6 +160,10 @@ __device__ __forceinline__ void store_env(const typename L::E &e, const Consts &
   si[(L::R + 1) * N + i] = (int32_t)e.episode;
   si[(L::R + 2) * N + i] = (int32_t)e.err;
   si[(L::R + 3) * N + i] = last_naughty;
+  if (k.goal_scoring) {
+#pragma unroll 1
+    for (int q = 0; q < L::E::kGoalDoubles; q++) si[(L::R + 4 + q) * N + i] = (int32_t)(unsigned)e.gs(q);
+  }
 }
 
 // Result rows of one warp: lane l holds `dim` values that belong at dst[l * dim .. l * dim + dim), so the warp's 32 rows
@@ -619,7 +628,7 @@ int rr_create(const rr_config *cfg, int64_t n_envs, int device, rr_sim **out) {
   s->NH = game ? 2 : 1; s->NG = game ? 2 : 0; s->NP = game ? 4 : 1; s->NN = game ? 4 : 0;
   s->R = s->NH + s->NG; s->B = s->NP + s->NN;
   s->NF = s->R * 10 + s->B * 8 + 2;
-  s->NI = s->R + 4;
+  s->NI = s->R + 4 + (cfg->goal_scoring ? 2 + 2 * s->B : 0);
   if (cudaMalloc(&s->start, sizeof(double) * (3 * s->R + 2 * s->B) * n_envs) != cudaSuccess ||
       cudaMalloc(&s->sf, sizeof(double) * (s->NF + prior_columns(s)) * n_envs) != cudaSuccess ||
       cudaMalloc(&s->si, sizeof(int32_t) * s->NI * n_envs) != cudaSuccess ||
@@ -974,7 +983,8 @@ int rr_set_state(rr_sim *s, const double *rob, const double *rhist, const int32_
   CK(cudaDeviceSynchronize());
   const int64_t N = s->N;
   const int R = s->R, B = s->B;
-  std::vector<double> sf((size_t)s->NF * N);
+  const int NFP = s->NF + prior_columns(s);
+  std::vector<double> sf((size_t)NFP * N);
   std::vector<int32_t> si((size_t)s->NI * N);
   CK(cudaMemcpy(si.data(), s->si, sizeof(int32_t) * si.size(), cudaMemcpyDeviceToHost));  // keep episode counters
   for (int64_t i = 0; i < N; i++) {
@@ -994,9 +1004,30 @@ int rr_set_state(rr_sim *s, const double *rob, const double *rhist, const int32_
       f += 8;
     }
     sf[(size_t)(f + 0) * N + i] = 0.0; sf[(size_t)(f + 1) * N + i] = 0.0;
+    f += 2;
+    if (prior_columns(s)) {
+      // rectDblPriorStep of the injected state = rectDbl.copy() of the injected pose, as every on_reset / on_step_begin
+      // leaves it (RR_Robot.py:83,117; RR_Ball.py:56,61,76; snapshot_prior_step in rr_sim.cuh): the observation of an
+      // injected state is then the same as the reference's ref_harness.inject(), which copies the rects too
+      for (int r = 0; r < R; r++, f += 3) {
+        const double *p = rob + (i * R + r) * 7;
+        sf[(size_t)(f + 0) * N + i] = norm_rot(p[6]);
+        sf[(size_t)(f + 1) * N + i] = 10.0 + (p[0] - 10.0);
+        sf[(size_t)(f + 2) * N + i] = 20.0 + (p[1] - 20.0);
+      }
+      for (int b = 0; b < B; b++, f += 2) {
+        const double *p = ball + (i * B + b) * 8;
+        sf[(size_t)(f + 0) * N + i] = 7.0 + (p[0] - 7.0);
+        sf[(size_t)(f + 1) * N + i] = 7.0 + (p[1] - 7.0);
+      }
+    }
     si[(size_t)(R + 0) * N + i] = step[i];
     si[(size_t)(R + 2) * N + i] = 0;
     si[(size_t)(R + 3) * N + i] = 0;
+    if (s->cfg.goal_scoring) {  // as after a reset: every ball alive, nothing tracked or scored
+      si[(size_t)(R + 4) * N + i] = (1 << B) - 1;
+      for (int q = 1; q < 2 + 2 * B; q++) si[(size_t)(R + 4 + q) * N + i] = 0;
+    }
   }
   CK(cudaMemcpy(s->sf, sf.data(), sizeof(double) * sf.size(), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(s->si, si.data(), sizeof(int32_t) * si.size(), cudaMemcpyHostToDevice));
@@ -1031,6 +1062,32 @@ int rr_get_state(rr_sim *s, double *rob, double *rhist, int32_t *rflag, double *
       f += 8;
     }
     step[i] = si[(size_t)(R + 0) * N + i];
+  }
+  return RR_OK;
+}
+
+int rr_goal_state(rr_sim *s, int32_t *alive_host, int32_t *score_host, int32_t *destroyed_host, int32_t *dwell_host) {
+  if (!s) return fail(RR_E_INVALID, "null handle");
+  if (!s->cfg.goal_scoring) return fail(RR_E_INVALID, "the handle was created without goal_scoring");
+  ON_DEVICE(s->device);
+  CK(cudaDeviceSynchronize());
+  const int64_t N = s->N;
+  const int R = s->R, B = s->B, G = 2 + 2 * B;
+  std::vector<int32_t> g((size_t)G * N);
+  CK(cudaMemcpy(g.data(), s->si + (size_t)(R + 4) * N, sizeof(int32_t) * g.size(), cudaMemcpyDeviceToHost));
+  const uint32_t bm = (1u << B) - 1u;
+  for (int64_t i = 0; i < N; i++) {
+    const uint32_t alive = (uint32_t)g[(size_t)0 * N + i], sc = (uint32_t)g[(size_t)1 * N + i];
+    if (alive_host) alive_host[i] = (int32_t)alive;
+    int destroyed = 0;
+    for (int q = 0; q < 2; q++) {  // Goal.get_score :87-88, is_destroyed :90-91
+      const int pos = __builtin_popcount((sc >> (2 * q * B)) & bm), neg = __builtin_popcount((sc >> ((2 * q + 1) * B)) & bm);
+      if (score_host) score_host[i * 2 + q] = 500 * (pos - neg);
+      if (neg >= 3) destroyed |= 1 << q;
+    }
+    if (destroyed_host) destroyed_host[i] = destroyed;
+    if (dwell_host)
+      for (int q = 0; q < 2 * B; q++) dwell_host[i * 2 * B + q] = g[(size_t)(2 + q) * N + i];
   }
   return RR_OK;
 }

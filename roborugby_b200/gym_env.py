@@ -65,14 +65,22 @@ class DebugInfo(dict):
 
 
 class _GoalView:
-    """sprHappyGoal / sprGrumpyGoal: scoring is dead code on the reference's live path
-    (SURVEY.md §0.4), so the score is 0 and a goal is never destroyed."""
+    """sprHappyGoal / sprGrumpyGoal (RR_Goal.py).  At the reference's HEAD scoring is dead code: the
+    score is 0 and a goal is never destroyed.  With goal_scoring=True (goal scoring as intended, include/rr_b200.h)
+    both reflect the env's goal bookkeeping."""
+
+    def __init__(self, env=None, index=0):
+        self._env, self._index = env, index
 
     def get_score(self):
-        return 0
+        if self._env is None:
+            return 0
+        return int(self._env._v.goal_state()["score"][0, self._index])
 
     def is_destroyed(self):
-        return False
+        if self._env is None:
+            return False
+        return bool(self._env._v.goal_state()["destroyed"][0, self._index])
 
 
 class _RectView:
@@ -145,14 +153,14 @@ class RoboRugbyEnv:
     reward_range = (-float("inf"), float("inf"))
 
     def __init__(self, env_id, preset="GAME", device="cuda:0", seed=0, time_limit=False, lst_starting_config=None,
-                 reward_mixins=None, observer=None):
+                 reward_mixins=None, observer=None, goal_scoring=False):
         """reward_mixins: names of RR_ScoreKeepers.py mixins in class-definition order, composed on top of `env_id`'s
         observer and action space the way main.py:42-49 composes ad-hoc classes (None: the id's own mixins)."""
         self.preset = get_preset(preset)
         self.time_limit = bool(time_limit)
         self._v = RoboRugbyVecEnv(env_id, 1, preset=self.preset, device=device, seed=seed, time_limit=time_limit,
                                   auto_reset=False, out_dtype=torch.float64, strict_reset=True,
-                                  reward_mixins=reward_mixins, observer=observer)
+                                  reward_mixins=reward_mixins, observer=observer, goal_scoring=goal_scoring)
         self.spec = EnvSpec(env_id, self._v.max_episode_steps)
         R = self._v.num_robots
         if self._v.discrete:
@@ -162,7 +170,8 @@ class RoboRugbyEnv:
             self.action_space = Box(-np.ones(n, np.float32), np.ones(n, np.float32), dtype=np.float32)
         hi = max(self.preset.arena_width, self.preset.arena_height, 360)  # RR_Observers.py:30-37
         self.observation_space = Box(-hi, hi, shape=(self._v.obs_dim,), dtype=np.float32) if self._v.obs_dim else None
-        self.sprHappyGoal, self.sprGrumpyGoal = _GoalView(), _GoalView()
+        self.sprHappyGoal = _GoalView(self, 0) if goal_scoring else _GoalView()
+        self.sprGrumpyGoal = _GoalView(self, 1) if goal_scoring else _GoalView()
         # entity lists the reference's scripts index into (main.py:59-63, RR_EnvBase.py:54-68)
         nh, npos = self.preset.num_robots_happy, self.preset.num_ball_pos
         self.lstRobots = [RobotView(self, i, TEAM_HAPPY if i < nh else TEAM_GRUMPY) for i in range(R)]
@@ -291,7 +300,12 @@ class RoboRugbyEnv:
         return self._reward[TEAM_HAPPY if int_team == TEAM_HAPPY else TEAM_GRUMPY]
 
     def game_is_done(self):  # RR_EnvBase.py:555-559
-        return int(self._v.get_state()["step"][0]) > self.spec.max_episode_steps
+        if int(self._v.get_state()["step"][0]) > self.spec.max_episode_steps:
+            return True
+        if not self._v.cfg.goal_scoring:
+            return False
+        g = self._v.goal_state()
+        return bool(g["destroyed"][0].any() or not g["alive"][0].any())
 
     @property
     def lngStepCount(self):

@@ -25,7 +25,8 @@ from .constants import ENV_IDS, get_preset
 class RoboRugbyVecEnv:
     def __init__(self, env_id="RoboRugbySimpleDuel-v2", num_envs=4096, preset="GAME", device="cuda:0", seed=0,
                  env_offset=0, time_limit=True, auto_reset=True, out_dtype=torch.float32, strict_reset=True,
-                 n_actions=None, observer=None, reward_mask=None, reward_order=None, reward_mixins=None, flags=0):
+                 n_actions=None, observer=None, reward_mask=None, reward_order=None, reward_mixins=None, flags=0,
+                 goal_scoring=False):
         if env_id not in ENV_IDS:
             raise ValueError(f"unknown env id {env_id!r}; expected one of {ENV_IDS}")
         if not torch.cuda.is_available():
@@ -54,6 +55,7 @@ class RoboRugbyVecEnv:
         if reward_order is not None:
             cfg.reward_order = int(reward_order)
         cfg.flags = int(flags)
+        cfg.goal_scoring = int(bool(goal_scoring))   # goal scoring as intended (include/rr_b200.h); default: the reference's HEAD
         cfg.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
         cfg.env_offset = int(env_offset)
         self.cfg = cfg
@@ -239,6 +241,17 @@ class RoboRugbyVecEnv:
         step = np.ascontiguousarray(st["step"], np.int32).reshape(N)
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         _lib.check(self.lib.rr_set_state(self._h, p(rob), p(rhist), p(rflag), p(ball), p(step)))
+
+    def goal_state(self):
+        """Goal bookkeeping (goal_scoring=True): dict of numpy arrays alive [N, B] (0/1), score [N, 2] (happy goal,
+        grumpy goal), destroyed [N, 2], dwell [N, 2, B]."""
+        N, B = self.num_envs, self.num_balls
+        alive = np.zeros(N, np.int32); score = np.zeros((N, 2), np.int32); destroyed = np.zeros(N, np.int32)
+        dwell = np.zeros((N, 2, B), np.int32)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        _lib.check(self.lib.rr_goal_state(self._h, p(alive), p(score), p(destroyed), p(dwell)))
+        return dict(alive=(alive[:, None] >> np.arange(B)) & 1, score=score,
+                    destroyed=(destroyed[:, None] >> np.arange(2)) & 1, dwell=dwell)
 
     def error_mask(self, clear=False):
         err = np.zeros(self.num_envs, np.uint32)

@@ -54,6 +54,8 @@ def lib():
         L.emul_observe_entity.restype = C.c_uint
         L.emul_assign_balls.argtypes = [C.POINTER(Config), vp, vp, vp, vp, vp, vp, C.c_int, vp]
         L.emul_assign_balls.restype = None
+        L.emul_goal_rollout.argtypes = [C.POINTER(Config), vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp, vp, vp]
+        L.emul_goal_rollout.restype = C.c_uint
         L.emul_step_k.argtypes = [C.POINTER(Config), vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]
         L.emul_step_k.restype = C.c_uint
         L.emul_last_replays.argtypes = []
@@ -105,6 +107,21 @@ class EmulEnv:
         err = lib().emul_step_k(C.byref(self.cfg), _p(self.rob), _p(self.rhist), _p(self.rflag), _p(self.ball),
                                 _p(self.stepc), _p(a), A, K, _p(rew), _p(cnt))
         return int(err), rew, cnt
+
+    def goal_rollout(self, actions):
+        """K steps on one Env object with the goal bookkeeping recorded after every step.  actions [K, A] with NaN for
+        absent commands.  Returns dict(err, steps (completed), rew [K, 2], alive [K] (mask), scored [K] (masks), done [K],
+        dwell [2, B] (final))."""
+        a = np.ascontiguousarray(np.asarray(actions, np.float64))
+        K, A = a.shape
+        n_act = np.ascontiguousarray((~np.isnan(a)).sum(1).astype(np.int32))
+        a = np.nan_to_num(a, nan=0.0)
+        rew = np.zeros((K, 2)); goal = np.zeros((K, 3), np.int32); dwell = np.zeros((2, self.B), np.int32)
+        done_steps = np.zeros(1, np.int32)
+        err = lib().emul_goal_rollout(C.byref(self.cfg), _p(self.rob), _p(self.rhist), _p(self.rflag), _p(self.ball),
+                                      _p(self.stepc), _p(a), _p(n_act), A, K, _p(rew), _p(goal), _p(dwell), _p(done_steps))
+        return dict(err=int(err), steps=int(done_steps[0]), rew=rew, alive=goal[:, 0], scored=goal[:, 1], done=goal[:, 2],
+                    dwell=dwell)
 
     def reset(self, env_index, episode, construct=False):
         return lib().emul_reset(C.byref(self.cfg), _p(self.rob), _p(self.rhist), _p(self.rflag), _p(self.ball),

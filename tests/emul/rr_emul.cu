@@ -42,6 +42,7 @@ static void load(E &e, const Consts &k, const double *rob, const double *rhist, 
   e.step = step; e.err = 0; e.episode = 0; e.ret_h = e.ret_g = 0;
   e.invalidate_caches();
   e.memo_clear();
+  e.goal_clear();
   e.sq_watch = 0; e.rr_stuck = 0;
 }
 
@@ -131,6 +132,47 @@ static unsigned step_k_t(const Consts &k, double *rob, double *rhist, int32_t *r
   return errs;
 }
 
+// step_k_t for both action kinds, with the goal bookkeeping (goal_scoring) recorded after every step:
+// goal[s] = {alive mask, scored masks, done flag}; dwell_out = final dwell counters [2][B]
+template <int NH, int NG, int NP, int NN>
+static unsigned goal_rollout_t(const Consts &k, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,
+                               const double *actions, const int32_t *n_act, int stride, int K, double *rew_out,
+                               int32_t *goal, int32_t *dwell_out, int32_t *steps_done) {
+  HostEnv<NH, NG, NP, NN> h;
+  auto &e = h.e;
+  using E = typename HostEnv<NH, NG, NP, NN>::E;
+  load(e, k, rob, rhist, rflag, ball, *step);
+  unsigned errs = 0;
+  *steps_done = 0;
+  for (int s = 0; s < K; s++) {
+    unsigned cmd = 0;
+    int n_cmd;
+    const double *a = actions + (size_t)s * stride;
+    if (k.discrete) {
+      n_cmd = n_act[s];
+      for (int r = 0; r < n_cmd && r < E::R; r++) {
+        int l, rt;
+        thrust_from_direction((int)a[r], l, rt);
+        cmd |= pack_thrust(r, l, rt);
+      }
+    } else {
+      n_cmd = n_act[s] / 2;
+      for (int r = 0; r < n_cmd && r < E::R; r++)
+        cmd |= pack_thrust(r, (int)rint((double)(float)a[2 * r]), (int)rint((double)(float)a[2 * r + 1]));
+    }
+    StepOut o;
+    sim_step(e, k, cmd, n_cmd, o, true);
+    errs |= o.step_err;
+    if (o.step_err) break;
+    rew_out[2 * s] = o.rew_h; rew_out[2 * s + 1] = o.rew_g;
+    goal[3 * s] = (int32_t)e.alive(); goal[3 * s + 1] = (int32_t)e.scored(); goal[3 * s + 2] = o.done;
+    *steps_done = s + 1;
+  }
+  for (int q = 0; q < 2 * E::B; q++) dwell_out[q] = (int32_t)e.gs(2 + q);
+  store(e, rob, rhist, rflag, ball, step);
+  return errs;
+}
+
 template <int NH, int NG, int NP, int NN>
 static unsigned reset_t(const Consts &k, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,
                         uint64_t env, uint32_t episode, int construct) {
@@ -168,6 +210,15 @@ unsigned emul_step_k(const rr_config *cfg, double *rob, double *rhist, int32_t *
   if (cfg->preset == RR_PRESET_GAME)
     return step_k_t<2, 2, 4, 4>(k, rob, rhist, rflag, ball, step, actions, n_actions, K, rew_out, counters);
   return step_k_t<1, 0, 1, 0>(k, rob, rhist, rflag, ball, step, actions, n_actions, K, rew_out, counters);
+}
+
+unsigned emul_goal_rollout(const rr_config *cfg, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,
+                           const double *actions, const int32_t *n_act, int stride, int K, double *rew_out, int32_t *goal,
+                           int32_t *dwell_out, int32_t *steps_done) {
+  Consts k = make_consts(*cfg);
+  if (cfg->preset == RR_PRESET_GAME)
+    return goal_rollout_t<2, 2, 4, 4>(k, rob, rhist, rflag, ball, step, actions, n_act, stride, K, rew_out, goal, dwell_out, steps_done);
+  return goal_rollout_t<1, 0, 1, 0>(k, rob, rhist, rflag, ball, step, actions, n_act, stride, K, rew_out, goal, dwell_out, steps_done);
 }
 
 unsigned emul_reset(const rr_config *cfg, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,

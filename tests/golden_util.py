@@ -9,7 +9,7 @@ STATE_KEYS = ("rob", "rhist", "rflag", "ball", "step")
 
 def parse_name(path):
     """GAME_RoboRugbySimpleDuel-v2_chase_s2.npz -> (preset, env_id, kind)."""
-    m = re.match(r"(GAME|TRAIN)_(RoboRugby[A-Za-z]*-v\d|DuelAllCoordsPrior|DuelAllCoords|DuelAllMixins|DuelCutChain|DuelLidar6v1)_([a-z]+)", os.path.basename(path))
+    m = re.match(r"(GAME|TRAIN)_(RoboRugby[A-Za-z]*-v\d|DuelAllCoordsPrior|DuelAllCoords|DuelAllMixins|DuelCutChain|DuelLidar6v1|DuelGoals)_([a-z]+)", os.path.basename(path))
     return m.group(1), m.group(2), m.group(3)
 
 
@@ -26,6 +26,7 @@ CUSTOM_MIXINS = {
                                                  "PushPosBallsToGoal", "ChasePosBall", "NaughtyBots"]),
     # NaughtyBots.on_step_end does not call super(): KeepMovingGuys, listed after it, never runs its on_step_end
     "DuelCutChain": ("RoboRugbySimpleDuel-v2", ["DontDriveInGoals", "ChasePosBall", "NaughtyBots", "KeepMovingGuys"]),
+    "DuelGoals": ("RoboRugbySimpleDuel-v2", ["BaseDestruction", "PushPosBallsToGoal", "ChasePosBall"]),
 }
 
 

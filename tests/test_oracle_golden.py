@@ -140,3 +140,50 @@ def test_oracle_entity_observations_and_stephen_assignment(oracle, path):
     if env.cfg.observer in (3, 4):
         with pytest.raises(NotImplementedError):
             env.observe_entity(0, 0)
+
+
+GOALS = golden_files("*_goals_*.npz")
+
+
+@pytest.mark.parametrize("path", GOALS, ids=[p.split("/")[-1] for p in GOALS])
+def test_oracle_goal_scoring_matches_patched_reference(oracle, path):
+    """Goal scoring as intended (cfg.goal_scoring): the reference with its dead scoring code made live by the in-memory
+    patches of oracle/ref_harness.py (_GOAL_SCORING_PATCHES: RR_Goal.py:54-91, RR_EnvBase.py:461-511).  Whole
+    trajectories from the first state: state, observations, rewards (they carry the +-500 score delta), done, and after
+    every step the balls still alive, both goals' scores and destroyed flags and the dwell counters, bit for bit."""
+    preset, env_id, _ = parse_name(path)
+    d = np.load(path)
+    n, T = d["act"].shape[:2]
+    base_id, observer = resolve_env(env_id)
+    cfg = apply_overrides(oracle.default_config(preset, base_id), env_id)
+    cfg.goal_scoring = 1
+    env = oracle.OracleEnv(cfg=cfg)
+    oracle.scratch_mode(0)
+    events = killed = ended = 0
+    for i in range(n):
+        env.set_state(state_at(d, i, 0))
+        for t in range(T):
+            if d["exc"][i, t] == 2:      # the reference's game_is_done() was already True: step() raises (:261-262)
+                assert env.step(actions_at(d, i, t))["err"] & 1, (i, t)
+                ended += 1
+                break
+            oracle.scratch_reset()
+            out = env.step(actions_at(d, i, t))
+            assert out["err"] == 0, (i, t, out["err"])
+            got, want = env.get_state(), state_at(d, i, t + 1)
+            assert states_equal(got, want), (i, t, state_diff(got, want))
+            assert _eq(out["obs_h"], d["obs_h"][i, t]) and _eq(out["obs_g"], d["obs_g"][i, t]), (i, t)
+            assert _eq(out["rew"], d["rew"][i, t]), (i, t, out["rew"], d["rew"][i, t])
+            assert out["done"] == int(d["done"][i, t]) and out["naughty"] == int(d["naughty"][i, t]), (i, t)
+            g = env.goal_state()
+            assert np.array_equal(g["alive"], d["alive"][i, t + 1]), (i, t)
+            assert np.array_equal(g["score"], d["score"][i, t + 1]) and np.array_equal(g["destroyed"], d["destroyed"][i, t + 1])
+            assert np.array_equal(g["dwell"], d["dwell"][i, t + 1]), (i, t, g["dwell"], d["dwell"][i, t + 1])
+            assert g["delta"] == int(d["delta"][i, t])
+            events += g["delta"] != 0
+        killed += int((d["alive"][i, -1] == 0).sum())
+    print(f"{path.split('/')[-1]}: {events} scoring steps, {killed} balls consumed, {ended} episodes ended by the goals")
+    if "SimpleDuel-v2" in path:   # NaughtyBots cuts the on_step_end chain before the goals' own hook: nothing ever scores
+        assert events == 0 and killed == 0 and d["dwell"].max() == 0
+    else:
+        assert events > 0 and killed > 0

@@ -693,3 +693,75 @@ def test_gpu_stephen_players_drive_the_full_game():
     assert o.shape == (11,) and one.get_game_state().shape == (11,)
     with pytest.raises(AssertionError):
         one.get_game_state(int_team=rr.TEAM_GRUMPY, obj_robot=one.lstHappyBots[0])
+
+
+GOALS = golden_files("*_goals_*.npz")
+
+
+@pytest.mark.parametrize("path", GOALS, ids=[p.split("/")[-1] for p in GOALS])
+def test_gpu_goal_scoring_matches_patched_reference(path):
+    """goal_scoring=1 through the C ABI: each trajectory of the patched reference (oracle/ref_harness.py
+    _GOAL_SCORING_PATCHES) is one env stepped in ONE fused launch; rewards (they carry the +-500 delta and the
+    BaseDestruction payout) and done per step, and rr_goal_state at the end: alive balls, both scores, destroyed
+    flags, dwell counters.  A trajectory whose float rewards leave the 1e-9 bar (chaotic drift over 165 chase steps)
+    is dropped from there and counted."""
+    preset, env_id, _ = parse_name(path)
+    d = np.load(path)
+    n, T = d["act"].shape[:2]
+    discrete = env_id != "RoboRugby-v0"
+    dropped = events = 0
+    for i in range(n):
+        over = np.nonzero(d["exc"][i] == 2)[0]
+        steps = int(over[0]) if len(over) else T
+        A = int((~np.isnan(d["act"][i, 0])).sum())
+        env = _venv(env_id, 1, preset, goal_scoring=True)
+        env.set_state({k: d[k][i, :1] for k in STATE_KEYS})
+        a = torch.as_tensor(d["act"][i, :steps, :A].astype(np.uint8 if discrete else np.float32)).reshape(steps, 1, A).cuda()
+        _, _, rew, done = env.step_k(a, steps)
+        rew, done = rew[:, 0].cpu().numpy(), done[:, 0].cpu().numpy()
+        assert env.error_mask()[0] == 0
+        bad = [t for t in range(steps) if not np.allclose(rew[t], d["rew"][i, t], rtol=1e-9, atol=1e-9)]
+        upto = bad[0] if bad else steps
+        assert np.array_equal(done[:upto], d["done"][i, :upto])
+        if bad:
+            dropped += 1
+        else:
+            g = env.goal_state()
+            assert np.array_equal(g["alive"][0], d["alive"][i, steps]) and np.array_equal(g["score"][0], d["score"][i, steps])
+            assert np.array_equal(g["destroyed"][0], d["destroyed"][i, steps]) and np.array_equal(g["dwell"][0], d["dwell"][i, steps])
+            events += int((d["delta"][i, :steps] != 0).sum())
+            if len(over):   # the game is over: one more step is refused ("Game is over. Go home.", RR_EnvBase.py:261-262)
+                env.step_k(a[:1], 1)
+                assert env.error_mask()[0] & 1
+        env.close()
+    print(f"{path.split('/')[-1]}: {n} trajectories, {dropped} dropped after a float deviation, {events} scoring steps verified")
+    assert dropped <= n // 2 and (events > 0 or "SimpleDuel-v2" in path)
+
+
+def test_gpu_goal_scoring_single_env_wrapper():
+    """The drop-in env with goal scoring as intended: sprHappyGoal.get_score() / is_destroyed() and game_is_done()
+    follow the bookkeeping; without the flag they are the reference's constants."""
+    import roborugby_b200 as rr
+    W = 800.0
+    spots = [(W - 40 - 35 * k, W - 40 - 30 * (k % 2)) for k in range(3)]
+    for seed in range(50):   # a random start whose robots and other balls are nowhere near the happy goal's corner
+        env = rr.RoboRugbyEnv("RoboRugby-v0", preset="GAME", goal_scoring=True, seed=seed)
+        st = env.get_state()
+        if (np.hypot(st["rob"][:, 0] - W, st["rob"][:, 1] - W) > 320).all() and \
+                (np.hypot(st["ball"][:, 0] - W, st["ball"][:, 1] - W) > 320).all():
+            break
+    for (x, y), b in zip(spots, (4, 5, 6)):   # three negative balls parked (at rest) in the happy goal
+        st["ball"][b] = (x, y, x - 7, x + 7, y - 7, y + 7, 0, 0)
+    env.set_state(st)
+    assert env.sprHappyGoal.get_score() == 0 and not env.game_is_done()
+    done, n = False, 0
+    while not done and n < 200:
+        _, _, done, _ = env.step([(0.0, 0.0)])
+        n += 1
+    # first seen at the end of step 1, TIME_BALL_IN_GOAL_STEPS = 150 steps later the third negative ball destroys the goal
+    assert n == 151 and done and env.sprHappyGoal.is_destroyed() and env.sprHappyGoal.get_score() == -1500
+    assert not env.sprGrumpyGoal.is_destroyed() and env.game_is_done()
+    with pytest.raises(Exception, match="Game is over"):
+        env.step([(0.0, 0.0)])
+    plain = rr.RoboRugbyEnv("RoboRugby-v0", preset="GAME")
+    assert plain.sprHappyGoal.get_score() == 0 and not plain.sprHappyGoal.is_destroyed()
