@@ -31,10 +31,10 @@ namespace rr {
 // wave.  The hot per-env doubles (robot rects) live in shared memory, [field][thread] with the block
 // size as stride: GAME 56 doubles x 448 threads = 196 KB; the cold ones (balls, history slots) in a
 // per-thread local array.
-template <int NH, int NG, int NP, int NN>
+template <int NH, int NG, int NP, int NN, bool GOALS = false>
 struct Launch {
   static constexpr int R = NH + NG, B = NP + NN;
-  using E = Env<NH, NG, NP, NN>;
+  using E = Env<NH, NG, NP, NN, GOALS>;
   // largest block: bounded by 227 KB of shared memory and by 65 536 registers per SM
   static constexpr int kMaxBlock = R > 1 ? 448 : 512;
   static constexpr int kTrigDoubles = kTrigRows * 4;  // sin/cos tables staged in front of the env fields
@@ -121,7 +121,7 @@ __device__ __forceinline__ void load_env(typename L::E &e, double *cold, const C
   e.episode = (unsigned)si[(L::R + 1) * N + i];
   e.err = (unsigned)si[(L::R + 2) * N + i];
   e.goal_clear();
-  if (k.goal_scoring) {  // goal bookkeeping: alive mask, scored masks, dwell counters [2][B] (extra int32 columns)
+  if constexpr (L::E::kGoals) {  // goal bookkeeping: alive mask, scored masks, dwell counters [2][B] (extra int32 columns)
 #pragma unroll 1
     for (int q = 0; q < L::E::kGoalDoubles; q++) e.gs(q) = (double)(unsigned)si[(L::R + 4 + q) * N + i];
   }
@@ -160,7 +160,7 @@ __device__ __forceinline__ void store_env(const typename L::E &e, const Consts &
   si[(L::R + 1) * N + i] = (int32_t)e.episode;
   si[(L::R + 2) * N + i] = (int32_t)e.err;
   si[(L::R + 3) * N + i] = last_naughty;
-  if (k.goal_scoring) {
+  if constexpr (L::E::kGoals) {
 #pragma unroll 1
     for (int q = 0; q < L::E::kGoalDoubles; q++) si[(L::R + 4 + q) * N + i] = (int32_t)(unsigned)e.gs(q);
   }
@@ -565,6 +565,8 @@ int rr_default_config(rr_config *c, int preset, const char *env_id) {
 
 using LGame = Launch<2, 2, 4, 4>;
 using LTrain = Launch<1, 0, 1, 0>;
+using LGameGoals = Launch<2, 2, 4, 4, true>;   // rr_config.goal_scoring = 1
+using LTrainGoals = Launch<1, 0, 1, 0, true>;
 
 // Every kernel uses more than the default 48 KB of dynamic shared memory: opt in once per device (rr_create), not per
 // launch (the attribute call costs more than a K = 1 launch's own CPU time).
@@ -583,19 +585,20 @@ static cudaError_t opt_in_shared_memory() {
 }
 
 // Launch KERNEL<L, ...> for the handle's preset with the block size picked for its batch.
+#define LAUNCH_ONE(LTYPE, s, st, KERNEL, ...)                                                               \
+  do {                                                                                                      \
+    using L = LTYPE;                                                                                        \
+    auto kern = KERNEL;                                                                                     \
+    const int blk = pick_block((s)->N, (s)->sms, L::kMaxBlock);                                             \
+    kern<<<(unsigned)(((s)->N + blk - 1) / blk), blk, L::smem_bytes(blk), st>>>(__VA_ARGS__);               \
+  } while (0)
 #define LAUNCH_PRESET(s, st, KERNEL, ...)                                                                   \
   do {                                                                                                      \
-    if ((s)->cfg.preset == RR_PRESET_GAME) {                                                                \
-      using L = LGame;                                                                                      \
-      auto kern = KERNEL;                                                                                   \
-      const int blk = pick_block((s)->N, (s)->sms, L::kMaxBlock);                                           \
-      kern<<<(unsigned)(((s)->N + blk - 1) / blk), blk, L::smem_bytes(blk), st>>>(__VA_ARGS__);             \
-    } else {                                                                                                \
-      using L = LTrain;                                                                                     \
-      auto kern = KERNEL;                                                                                   \
-      const int blk = pick_block((s)->N, (s)->sms, L::kMaxBlock);                                           \
-      kern<<<(unsigned)(((s)->N + blk - 1) / blk), blk, L::smem_bytes(blk), st>>>(__VA_ARGS__);             \
-    }                                                                                                       \
+    const bool game_ = (s)->cfg.preset == RR_PRESET_GAME, goals_ = (s)->cfg.goal_scoring != 0;              \
+    if (game_ && !goals_) LAUNCH_ONE(LGame, s, st, KERNEL, __VA_ARGS__);                                    \
+    else if (!game_ && !goals_) LAUNCH_ONE(LTrain, s, st, KERNEL, __VA_ARGS__);                             \
+    else if (game_) LAUNCH_ONE(LGameGoals, s, st, KERNEL, __VA_ARGS__);                                     \
+    else LAUNCH_ONE(LTrainGoals, s, st, KERNEL, __VA_ARGS__);                                               \
   } while (0)
 
 // columns of sf behind the base state: rectDblPriorStep poses, kept only for the observer that reports them
@@ -639,7 +642,8 @@ int rr_create(const rr_config *cfg, int64_t n_envs, int device, rr_sim **out) {
   }
   s->stats = s->own_stats;
   {
-    cudaError_t ae = game ? opt_in_shared_memory<LGame>() : opt_in_shared_memory<LTrain>();
+    cudaError_t ae = cfg->goal_scoring ? (game ? opt_in_shared_memory<LGameGoals>() : opt_in_shared_memory<LTrainGoals>())
+                                       : (game ? opt_in_shared_memory<LGame>() : opt_in_shared_memory<LTrain>());
     if (ae != cudaSuccess) { rr_destroy(s); return fail(RR_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(ae)); }
   }
   if (cudaMemset(s->stats, 0, sizeof(double) * RR_NUM_STATS) != cudaSuccess) { rr_destroy(s); return fail(RR_E_CUDA, "cudaMemset failed"); }

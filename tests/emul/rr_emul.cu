@@ -10,9 +10,9 @@
 
 using namespace rr;
 
-template <int NH, int NG, int NP, int NN>
+template <int NH, int NG, int NP, int NN, bool G = false>
 struct HostEnv {
-  using E = Env<NH, NG, NP, NN>;
+  using E = Env<NH, NG, NP, NN, G>;
   double buf[E::kDoubles];
   double cold[E::kColdDoubles];
   E e;
@@ -67,13 +67,13 @@ static double g_last_replays = 0.0;  // frames of the last emul_step answered by
 static double g_last_whole = 0.0;    // ... of which whole frames
 static double g_last_stuck = 0.0;    // robot-robot phases answered by the stuck-pair memo
 
-template <int NH, int NG, int NP, int NN>
+template <int NH, int NG, int NP, int NN, bool G = false>
 static unsigned step_t(const Consts &k, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,
                        const double *actions, int n_actions, double *obs_h, double *obs_g, double *rew, int32_t *done,
                        int32_t *naughty) {
-  HostEnv<NH, NG, NP, NN> h;
+  HostEnv<NH, NG, NP, NN, G> h;
   auto &e = h.e;
-  using E = typename HostEnv<NH, NG, NP, NN>::E;
+  using E = typename HostEnv<NH, NG, NP, NN, G>::E;
   load(e, k, rob, rhist, rflag, ball, *step);
   unsigned cmd = 0;
   int n_cmd;
@@ -106,12 +106,12 @@ static unsigned step_t(const Consts &k, double *rob, double *rhist, int32_t *rfl
 
 // K discrete env-steps in one call on ONE Env object: like a fused GPU launch, the per-thread memo state (squeeze
 // memo, stuck-pair memo) lives across the steps.  Returns the OR of the steps' error bits; stops at the first error.
-template <int NH, int NG, int NP, int NN>
+template <int NH, int NG, int NP, int NN, bool G = false>
 static unsigned step_k_t(const Consts &k, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,
                          const double *actions, int n_actions, int K, double *rew_out, double *counters) {
-  HostEnv<NH, NG, NP, NN> h;
+  HostEnv<NH, NG, NP, NN, G> h;
   auto &e = h.e;
-  using E = typename HostEnv<NH, NG, NP, NN>::E;
+  using E = typename HostEnv<NH, NG, NP, NN, G>::E;
   load(e, k, rob, rhist, rflag, ball, *step);
   unsigned errs = 0;
   for (int s = 0; s < K; s++) {
@@ -134,13 +134,13 @@ static unsigned step_k_t(const Consts &k, double *rob, double *rhist, int32_t *r
 
 // step_k_t for both action kinds, with the goal bookkeeping (goal_scoring) recorded after every step:
 // goal[s] = {alive mask, scored masks, done flag}; dwell_out = final dwell counters [2][B]
-template <int NH, int NG, int NP, int NN>
+template <int NH, int NG, int NP, int NN, bool G = false>
 static unsigned goal_rollout_t(const Consts &k, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,
                                const double *actions, const int32_t *n_act, int stride, int K, double *rew_out,
                                int32_t *goal, int32_t *dwell_out, int32_t *steps_done) {
-  HostEnv<NH, NG, NP, NN> h;
+  HostEnv<NH, NG, NP, NN, G> h;
   auto &e = h.e;
-  using E = typename HostEnv<NH, NG, NP, NN>::E;
+  using E = typename HostEnv<NH, NG, NP, NN, G>::E;
   load(e, k, rob, rhist, rflag, ball, *step);
   unsigned errs = 0;
   *steps_done = 0;
@@ -173,10 +173,10 @@ static unsigned goal_rollout_t(const Consts &k, double *rob, double *rhist, int3
   return errs;
 }
 
-template <int NH, int NG, int NP, int NN>
+template <int NH, int NG, int NP, int NN, bool G = false>
 static unsigned reset_t(const Consts &k, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,
                         uint64_t env, uint32_t episode, int construct) {
-  HostEnv<NH, NG, NP, NN> h;
+  HostEnv<NH, NG, NP, NN, G> h;
   auto &e = h.e;
   if (construct) construct_env(e);
   else load(e, k, rob, rhist, rflag, ball, *step);
@@ -198,6 +198,11 @@ unsigned emul_step(const rr_config *cfg, double *rob, double *rhist, int32_t *rf
                    int32_t *naughty) {
   Consts k = make_consts(*cfg);
   k.n_actions = n_actions;
+  if (cfg->goal_scoring) {
+    if (cfg->preset == RR_PRESET_GAME)
+      return step_t<2, 2, 4, 4, true>(k, rob, rhist, rflag, ball, step, actions, n_actions, obs_h, obs_g, rew, done, naughty);
+    return step_t<1, 0, 1, 0, true>(k, rob, rhist, rflag, ball, step, actions, n_actions, obs_h, obs_g, rew, done, naughty);
+  }
   if (cfg->preset == RR_PRESET_GAME)
     return step_t<2, 2, 4, 4>(k, rob, rhist, rflag, ball, step, actions, n_actions, obs_h, obs_g, rew, done, naughty);
   return step_t<1, 0, 1, 0>(k, rob, rhist, rflag, ball, step, actions, n_actions, obs_h, obs_g, rew, done, naughty);
@@ -217,8 +222,8 @@ unsigned emul_goal_rollout(const rr_config *cfg, double *rob, double *rhist, int
                            int32_t *dwell_out, int32_t *steps_done) {
   Consts k = make_consts(*cfg);
   if (cfg->preset == RR_PRESET_GAME)
-    return goal_rollout_t<2, 2, 4, 4>(k, rob, rhist, rflag, ball, step, actions, n_act, stride, K, rew_out, goal, dwell_out, steps_done);
-  return goal_rollout_t<1, 0, 1, 0>(k, rob, rhist, rflag, ball, step, actions, n_act, stride, K, rew_out, goal, dwell_out, steps_done);
+    return goal_rollout_t<2, 2, 4, 4, true>(k, rob, rhist, rflag, ball, step, actions, n_act, stride, K, rew_out, goal, dwell_out, steps_done);
+  return goal_rollout_t<1, 0, 1, 0, true>(k, rob, rhist, rflag, ball, step, actions, n_act, stride, K, rew_out, goal, dwell_out, steps_done);
 }
 
 unsigned emul_reset(const rr_config *cfg, double *rob, double *rhist, int32_t *rflag, double *ball, int32_t *step,

@@ -559,11 +559,13 @@ def test_gpu_bench_configuration_matches_oracle(oracle, strict):
     env.close()
 
 
+@pytest.mark.parametrize("fused", [True, False], ids=["one_launch", "launch_per_step"])
 @pytest.mark.parametrize("preset", ["GAME", "TRAIN"])
-def test_gpu_squeeze_memo_replay_is_exact(oracle, preset):
-    """The squeeze memo (rr_sim.cuh squeeze_contacts) on the GPU: 1 536 pinned-ball states, 6 fused steps, with the memo
-    and with RR_FLAG_NO_SQUEEZE_MEMO: every output row and the final state must be bit-identical, the memo must have
-    answered most of the pinned frames (RR_STAT_REPLAYS), and a sample is checked against the oracle."""
+def test_gpu_squeeze_memo_replay_is_exact(oracle, preset, fused):
+    """The squeeze memo (rr_sim.cuh squeeze_contacts) on the GPU: 1 536 pinned-ball states, 6 steps (fused in one launch,
+    or one launch per step), with the memo and with RR_FLAG_NO_SQUEEZE_MEMO: every output row and the final state must
+    be bit-identical, the memo must have answered most of the pinned frames (RR_STAT_REPLAYS), and a sample is checked
+    against the oracle."""
     from roborugby_b200 import _lib
     from squeeze_util import actions, oracle_env, pincer_env, scenario, stuck_pair_env
     rng = np.random.default_rng(5)
@@ -593,7 +595,11 @@ def test_gpu_squeeze_memo_replay_is_exact(oracle, preset):
     for flags in (0, _lib.FLAG_NO_SQUEEZE_MEMO):
         env = _venv(V2, N, preset, flags=flags)
         env.set_state(pool)
-        out = [x.clone() for x in env.step_k(a, K)]
+        if fused:
+            out = [x.clone() for x in env.step_k(a, K)]
+        else:   # one launch per env-step: the memo record travels from launch to launch through HBM (load_env / store_env)
+            rows = [[x.clone() for x in env.step_k(a[t:t + 1], 1)] for t in range(K)]
+            out = [torch.cat([r[j] for r in rows]) for j in range(4)]
         torch.cuda.synchronize()
         res.append((env.get_state(), out, env.error_mask(), env.get_stats()))
         env.close()
@@ -765,3 +771,23 @@ def test_gpu_goal_scoring_single_env_wrapper():
         env.step([(0.0, 0.0)])
     plain = rr.RoboRugbyEnv("RoboRugby-v0", preset="GAME")
     assert plain.sprHappyGoal.get_score() == 0 and not plain.sprHappyGoal.is_destroyed()
+
+
+def test_gpu_error_rate_of_random_rollouts_is_bounded():
+    """Steps on which the reference raises (or would never return: RR_EnvBase.py:415-421) end the episode with an error
+    bit and are auto-reset.  On the bench workload (random actions, reference placement) that is about 0.5 per million
+    env-steps (bench.py reports `errors_per_million_env_steps`); a regression of the contact code would show here."""
+    N, K = 65536, 32
+    env = _venv(V2, N, "GAME", seed=2026, time_limit=True, auto_reset=True, out_dtype=torch.float32)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for it in range(4):
+        acts = torch.randint(0, 8, (K, N, env.num_robots), generator=g, dtype=torch.uint8, device="cuda")
+        env.step_k(acts, K)
+    st = env.get_stats()
+    rate = 1e6 * st["errors"] / st["steps"]
+    print(f"{int(st['errors'])} error steps in {int(st['steps'])} env-steps: {rate:.2f} per million; "
+          f"{int(st['squeeze_replays'])} frames replayed by the squeeze memo")
+    assert st["steps"] == N * K * 4 and rate < 10.0
+    errs = env.error_mask()
+    assert (errs != 0).sum() <= st["errors"]     # sticky per-env masks: at most one per error step
+    env.close()
