@@ -40,14 +40,15 @@ FUSED = 32
 # capture of the committed kernel (profiles/, see PROFILE_SOURCE): dram__bytes_read.sum + dram__bytes_write.sum
 # (reported as roofline.traffic when the bench runs that exact workload) and the pipe / issue / SM-busy figures that
 # bound the kernel (reported as roofline.secondary; the path is not HBM-bound).
-PROFILE_SOURCE = {"GAME": "profiles/r01_v13_k_step_game_by_function.txt", "TRAIN": "profiles/r01_v13_k_step_train_by_function.txt"}
-NCU_TRAFFIC_BYTES = {"GAME": 1513.4e6, "TRAIN": 117.5e6}
+PROFILE_SOURCE = {"GAME": "profiles/r02_k_step_game_by_function.txt", "TRAIN": "profiles/r02_k_step_train_by_function.txt"}
+NCU_TRAFFIC_BYTES = {"GAME": 267.35e6 + 1773.45e6, "TRAIN": 15.57e6 + 114.23e6}
 NCU_SECONDARY = {
-    "GAME": {"fp64_pipe_pct": 17.0, "issue_slots_busy_pct": 27.6, "warps_active_pct": 21.8, "sm_busy_frac": 0.43,
-             "barrier_stall_per_issue": 3.87, "long_scoreboard_per_issue": 2.04},
-    "TRAIN": {"fp64_pipe_pct": 25.3, "issue_slots_busy_pct": 38.3},
+    "GAME": {"fp64_pipe_pct": 15.5, "issue_slots_busy_pct": 26.3, "warps_active_pct": 21.8, "sm_busy_frac": 0.863,
+             "barrier_stall_per_issue": 3.68, "long_scoreboard_per_issue": 2.72, "threads_per_instruction": 21.0},
+    "TRAIN": {"fp64_pipe_pct": 17.2, "issue_slots_busy_pct": 31.9, "warps_active_pct": 21.8, "sm_busy_frac": 0.887,
+              "barrier_stall_per_issue": 2.60, "long_scoreboard_per_issue": 0.92, "threads_per_instruction": 22.7},
 }
-KERNEL_NAME = {"GAME": "rr::k_step<rr::Launch<2,2,4,4>,float>", "TRAIN": "rr::k_step<rr::Launch<1,0,1,0>,float>"}
+KERNEL_NAME = {"GAME": "rr::k_step<rr::Launch<2, 2, 4, 4, 0>, float>", "TRAIN": "rr::k_step<rr::Launch<1, 0, 1, 0, 0>, float>"}
 # The Python reference itself (unmodified, stub pygame/gym) cannot travel to the GPU box; its own rate, measured in the
 # build container with oracle/time_reference.py (8 cores, one process per core), is recorded beside the port's.
 PY_REFERENCE_NOTE = {"GAME": "Python reference (oracle/time_reference.py, build container, 8 cores): 123 env-steps/s (18.9 per core)",
@@ -311,6 +312,7 @@ def main():
     stats = env.reduce_stats()  # the one optional collective: 64-byte all-reduce of episode statistics
     err_envs = int((env.error_mask() != 0).sum())
     local_stats = env.get_stats()
+    state_bytes = env.state_bytes_per_env
 
     # ---------------- extras: one env-step per launch (env.step()), DQN loop ----------------
     extras = {"per_rank_kernel_ms": per_rank_ms}
@@ -334,11 +336,12 @@ def main():
                         "note": "one env-step per launch (RoboRugbyVecEnv.step / GameEnv.step, RR_EnvBase.py:260), "
                                 "actions resident, back-to-back launches, no L2 flush"}
         if rank == 0 and world == 1:
-            extras["dqn"] = dqn_rate(dev, envs=4096, steps=120)
+            env.close()   # (its buffers are not needed any more)
+            extras["dqn"] = dqn_rate(dev, envs=16384, steps=60)
 
     if rank == 0:
         peak, peak_src = _peaks()
-        S = env.state_bytes_per_env
+        S = state_bytes
         q = 2.0 * S / K + act_bytes + 2 * D * 4 + 2 * 4 + 1  # algorithmic bytes per env-step
         bytes_per_launch = q * n_local * K
         avg_kernel_s = (sum(kernel_ms) / len(kernel_ms)) * 1e-3
@@ -370,7 +373,7 @@ def main():
         if cpu_baseline is not None:
             line["cpu_baseline"] = cpu_baseline
         print(json.dumps(line), flush=True)
-    env.close()
+    env.close()   # (idempotent)
     if world > 1:
         dist.destroy_process_group()
 
