@@ -8,15 +8,17 @@ Workload (BASELINE.json configs[2]): RoboRugbySimpleDuel-v2, 65 536 envs per GPU
 constants, uniformly random discrete actions for all four robots, fused launches of 32 env-steps
 with in-kernel auto-reset.  One bench "step" = one fused launch = 65 536 x 32 env-steps per GPU.
 
-  value    whole-job env-steps/s, inputs (actions) already resident in HBM, CUDA-event timed,
-           max over ranks, L2 flushed between timed launches
-  e2e      the same launches through the HOST-buffer C-ABI entry point rr_step_host: actions copied
-           host->device and observations/rewards/done copied device->host inside the timed region
+  value    whole-job env-steps/s, inputs (actions) already resident in HBM, CUDA-event timed over the whole region
+           (calls issued back to back; with the sub-batch pipeline, rr_set_pipeline, the groups of consecutive calls
+           overlap), max over ranks, L2 flushed in front of every launch
+  e2e      the same calls through the HOST-buffer C-ABI entry points rr_step_host_begin / _end (three calls in flight):
+           actions copied host->device, observations/rewards/done written into pinned host memory and read by the
+           caller after every call, all inside the timed region
   roofline HBM: algorithmic bytes per launch / measured kernel time vs MEASURED_PEAKS.json; `secondary` carries the
            ncu figures that actually bound the kernel (fp64 pipe, issue slots, SM busy) and the file they come from
   cpu_baseline  the C oracle (port of the reference algorithm, oracle/) on the host cores, N=1 only
   extras   k1: the same batch stepped ONE env-step per launch (env.step(), the call a policy-in-the-loop consumer
-           makes); dqn: env-steps/s inside the vectorised DQN loop (BASELINE configs[4]); per_rank_kernel_ms (N > 1)
+           makes); dqn: env-steps/s inside the vectorised DQN loop (BASELINE configs[4]); per_rank_ms_per_call (N > 1); single_launch: the same calls without the sub-batch pipeline
 
 --impl reference times the reference algorithm's CPU implementation on the host cores (the C
 oracle port; the Python reference itself cannot travel to the GPU box — its measured rate in the
@@ -36,6 +38,7 @@ sys.path.insert(0, ROOT)
 ENV_ID = "RoboRugbySimpleDuel-v2"
 ENVS_PER_GPU = 65536
 FUSED = 32
+PIPELINE = 128  # sub-batch groups (rr_set_pipeline): a group held back by its slowest env delays only its own next launch
 # Figures of ONE k_step launch of the bench workload (65 536 envs x 32 steps) from the committed `ncu --set full`
 # capture of the committed kernel (profiles/, see PROFILE_SOURCE): dram__bytes_read.sum + dram__bytes_write.sum
 # (reported as roofline.traffic when the bench runs that exact workload) and the pipe / issue / SM-busy figures that
@@ -171,7 +174,9 @@ def workload_config(args, world):
                         f"{'continuous thrust' if args.env_id == 'RoboRugby-v0' else 'discrete'} actions, "
                         f"{args.fused} fused env-steps per launch, auto-reset (BASELINE configs[{3 if args.env_id == 'RoboRugby-v0' else 2}])",
             "env_id": args.env_id, "preset": args.preset, "envs_per_gpu": args.envs, "fused_steps": args.fused,
-            "parallelism": f"env-shard x{world} (no data-path collective)", "l2": "flushed between timed launches",
+            "parallelism": f"env-shard x{world} (no data-path collective)", "pipeline_groups": args.pipeline,
+            "l2": "flushed: every launch is preceded, on its own stream, by a memset of its share of a 256 MB buffer "
+                  "(rr_set_flush_buffer), inside the timed region",
             "strict_reset": not args.relaxed_reset, "squeeze_memo": not args.no_squeeze_memo, "out_dtype": "float32"}
 
 
@@ -184,6 +189,8 @@ def main():
     ap.add_argument("--preset", default="GAME", choices=["GAME", "TRAIN"])
     ap.add_argument("--envs", type=int, default=ENVS_PER_GPU)
     ap.add_argument("--fused", type=int, default=FUSED)
+    ap.add_argument("--pipeline", type=int, default=PIPELINE, help="sub-batch groups stepped on their own streams "
+                    "(rr_set_pipeline); 1 = one stream-ordered launch per call, the round-1 measurement")
     ap.add_argument("--env-id", default=ENV_ID, help="another registered id, e.g. RoboRugby-v0 (the full game: continuous "
                     "thrust pairs for all robots, BASELINE configs[3]); the default is the workload the metric is quoted on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -258,46 +265,61 @@ def main():
     st["step"][:] = (np.arange(n_local) * 7919) % max(env.max_episode_steps - 1, 1)
     env.set_state(st)
 
+    env.set_pipeline(args.pipeline)
+    env.set_flush_buffer(flush)
     for w in range(args.warmup):
         env.step_k(acts[w % n_sets], K)
     barrier()
 
     # ---------------- device-resident timing (value) ----------------
+    # The calls are issued back to back; with a sub-batch pipeline the groups of call n + 1 start as their own group of
+    # call n finishes (no join in between), so the whole region is timed with one event pair on the issuing stream:
+    # start before the first call, end after the join behind the last one.
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = env.launch_count
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_wall0 = time.perf_counter()
+    e0.record()
     for s in range(args.steps):
-        flush.fill_(s & 0xff)  # evict state/action lines from L2 (outside the timed event pair)
-        ev[s][0].record()
-        env.step_k(acts[s % n_sets], K)
-        ev[s][1].record()
+        env.step_k(acts[s % n_sets], K, join=False)
+    env.join()
+    e1.record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = env.launch_count - launches0
-    kernel_ms = [a.elapsed_time(b) for a, b in ev]
-    my_ms = sum(kernel_ms)
+    my_ms = e0.elapsed_time(e1)
+    kernel_ms = [my_ms / args.steps] * args.steps
     t = torch.tensor([my_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     max_ms = float(t.item())
     value = total * K * args.steps / (max_ms * 1e-3)
     per_rank_ms = [my_ms / args.steps]
-    if world > 1:  # per-rank mean launch time: the max over ranks is the shard with the slowest envs (no collective inside)
+    if world > 1:  # per-rank mean time per call: the max over ranks is the shard with the slowest envs (no collective inside)
         allms = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
         dist.all_gather(allms, torch.tensor([my_ms / args.steps], dtype=torch.float64, device=dev))
         per_rank_ms = [float(x.item()) for x in allms]
 
-    # ---------------- end-to-end through the host-buffer C-ABI entry point ----------------
-    e2e_steps = max(3, min(args.steps, 10))
-    out = env.step_host(acts_host[0], K)  # allocates pinned result buffers + device staging
+    # ---------------- end-to-end through the host-buffer C-ABI entry points ----------------
+    # rr_step_host_begin / _end with three calls in flight: actions travel host->device, the kernels write the result rows
+    # straight into pinned host memory, and the caller reads every call's result on the host before it ends the next one.
+    e2e_steps = max(3, min(args.steps, 30))
+    depth = 3  # calls in flight (of at most RR_HOST_TICKETS = 4)
+    for w in range(4):  # allocates the sets of pinned result buffers + the device staging of all four tickets
+        env.step_host_end(env.step_host_begin(acts_host[w % n_sets], K, w % depth))
     barrier()
     t0 = time.perf_counter()
+    pending = [env.step_host_begin(acts_host[s % n_sets], K, s % depth) for s in range(min(depth - 1, e2e_steps))]
     for s in range(e2e_steps):
-        out = env.step_host(acts_host[s % n_sets], K)
+        nx = s + depth - 1
+        if nx < e2e_steps:
+            pending.append(env.step_host_begin(acts_host[nx % n_sets], K, nx % depth))
+        out = env.step_host_end(pending.pop(0))
         _ = float(out["rew"][K - 1, 0, 0])  # the caller reads the step's result on the host
+        if os.environ.get("RR_BENCH_TRACE"):
+            print("e2e call", s, round((time.perf_counter() - t0) * 1e3, 2), file=sys.stderr)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -315,8 +337,28 @@ def main():
     state_bytes = env.state_bytes_per_env
 
     # ---------------- extras: one env-step per launch (env.step()), DQN loop ----------------
-    extras = {"per_rank_kernel_ms": per_rank_ms}
+    extras = {"per_rank_ms_per_call": per_rank_ms}
     if not args.no_extras:
+        # (a) the same calls one stream-ordered launch at a time (no pipeline): the round-1 definition of `value`
+        env.set_pipeline(1)
+        for w in range(2):
+            env.step_k(acts[w % n_sets], K)
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+        for s, (a0, a1) in enumerate(ev):
+            a0.record(); env.step_k(acts[s % n_sets], K); a1.record()
+        barrier()
+        single_ms = [a0.elapsed_time(a1) for a0, a1 in ev]
+        t = torch.tensor([sum(single_ms)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        extras["single_launch"] = {"value": total * K * len(ev) / (float(t.item()) * 1e-3), "unit": UNIT,
+                                   "ms_per_launch": float(t.item()) / len(ev), "launches": len(ev),
+                                   "note": "pipeline_groups = 1: every call is one kernel over the whole batch and ends with "
+                                           "its slowest env; per-launch CUDA events, flush memset inside"}
+        env.set_flush_buffer(None)
+        # (b) one env-step per call (env.step()), back to back, 16 groups
+        env.set_pipeline(min(16, args.pipeline))
         n1 = 256
         a1 = [a[j:j + 1] for a in acts for j in range(K)]  # the same action stream as above, one row per launch
         for w in range(5):
@@ -325,16 +367,17 @@ def main():
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for s in range(n1):
-            env.step_k(a1[(5 + s) % len(a1)], 1)
+            env.step_k(a1[(5 + s) % len(a1)], 1, join=False)
+        env.join()
         e1.record()
         barrier()
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         extras["k1"] = {"value": total * n1 / (float(t.item()) * 1e-3), "unit": UNIT, "launches": n1,
-                        "ms_per_launch": float(t.item()) / n1,
-                        "note": "one env-step per launch (RoboRugbyVecEnv.step / GameEnv.step, RR_EnvBase.py:260), "
-                                "actions resident, back-to-back launches, no L2 flush"}
+                        "ms_per_launch": float(t.item()) / n1, "pipeline_groups": min(16, args.pipeline),
+                        "note": "one env-step per call (RoboRugbyVecEnv.step / GameEnv.step, RR_EnvBase.py:260), "
+                                "actions resident, calls issued back to back, no L2 flush"}
         if rank == 0 and world == 1:
             env.close()   # (its buffers are not needed any more)
             extras["dqn"] = dqn_rate(dev, envs=16384, steps=60)
@@ -351,7 +394,7 @@ def main():
             "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps},
+                    "steps": e2e_steps, "calls_in_flight": 3},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (NCU_TRAFFIC_BYTES[args.preset] if (args.envs, args.fused) == (ENVS_PER_GPU, FUSED)

@@ -193,6 +193,39 @@ int rr_step(rr_sim *s, const void *actions_dev, int32_t n_actions, int32_t k_ste
 int rr_step_host(rr_sim *s, const void *actions_host, int32_t n_actions, int32_t k_steps,
                  void *obs_h_host, void *obs_g_host, void *rew_host, uint8_t *done_host, void *stream);
 
+/* Sub-batch pipeline.  A launch is one wave of blocks and ends with its slowest env (a ball pinned between a robot and
+ * a wall costs its block several normal frames per physics frame): at the BASELINE configuration the mean block is done
+ * after 14 ms of a 17 ms launch.  rr_set_pipeline(s, n) splits the batch's blocks into n contiguous groups; every
+ * rr_step then launches one kernel per group on the handle's own streams, so a group that is held back delays only its
+ * OWN next launch while the SMs it leaves idle run the next launch of groups that have finished.  Results do not depend
+ * on n (envs never interact; the statistics are accumulated atomically).
+ * With n > 1 rr_step is asynchronous with respect to `stream`: the groups wait for the work `stream` holds at the
+ * time of the call (the actions, earlier resets, ...), but `stream` does not wait for them.  rr_join(s, stream) makes
+ * `stream` wait (on the device, without blocking the host) for everything issued so far; call it before reading
+ * results or the state on `stream`.  Every other entry point that takes a stream joins by itself, and those that
+ * synchronise the device cover the groups too, so only back-to-back rr_step calls overlap.  n = 1 (the default)
+ * restores the single stream-ordered launch.  Replaces: nothing in the reference (one env per process); it is the
+ * batched counterpart of running several reference envs in separate processes (Training_DQN_pytorch.py runs one). */
+int rr_set_pipeline(rr_sim *s, int32_t sub_batches);
+int rr_join(rr_sim *s, void *stream);
+
+/* Benchmark hygiene (bench.py): a device buffer larger than the L2 that is overwritten in front of every rr_step launch,
+ * on the stream that launches (with a sub-batch pipeline every group writes its share in front of its own launch), so
+ * that no state or action line survives in the L2 from one launch to the next.  bytes = 0 switches it off (default). */
+int rr_set_flush_buffer(rr_sim *s, void *buf_dev, int64_t bytes);
+
+/* rr_step_host with up to RR_HOST_TICKETS calls in flight: _begin enqueues a call and returns a ticket (0 ..
+ * RR_HOST_TICKETS - 1, handed out round robin) at once, _end blocks until that call's results are in host memory.
+ * The result buffers must be pinned (page-locked and mapped); the kernels write into them directly.  The caller
+ * rotates as many sets of result buffers as it keeps calls in flight and may begin calls n + 1, n + 2, ... before
+ * ending call n (results complete in order); a _begin that finds its ticket still in use first waits for that call.  With a sub-batch pipeline the groups of
+ * call n + 1 start while call n's slowest group still runs.  Action buffers are copied before _begin returns control
+ * of them only in stream order: keep them unchanged until the call has ended. */
+#define RR_HOST_TICKETS 4
+int rr_step_host_begin(rr_sim *s, const void *actions_host, int32_t n_actions, int32_t k_steps, void *obs_h_host,
+                       void *obs_g_host, void *rew_host, uint8_t *done_host, int32_t *ticket);
+int rr_step_host_end(rr_sim *s, int32_t ticket);
+
 /* Complete physics state, HOST buffers, array-of-structs layout used by the parity harness
  * (oracle/ref_harness.py): rob[N][R][7] = cx,cy,left,right,top,bottom,rot (FloatRect fields,
  * MyUtils.py:122-130); rhist[N][R][3] = pose in history slot count-1 (RR_Robot.py:43-58);

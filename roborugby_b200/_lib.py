@@ -63,6 +63,11 @@ SIGNATURES = {
     "rr_assign_balls": (C.c_int, [_vp, _vp, _i32, _vp, _vp]),
     "rr_step": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
     "rr_step_host": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "rr_set_pipeline": (C.c_int, [_vp, _i32]),
+    "rr_join": (C.c_int, [_vp, _vp]),
+    "rr_set_flush_buffer": (C.c_int, [_vp, _vp, _i64]),
+    "rr_step_host_begin": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp, C.POINTER(_i32)]),
+    "rr_step_host_end": (C.c_int, [_vp, _i32]),
     "rr_set_state": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "rr_get_state": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
     "rr_goal_state": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),

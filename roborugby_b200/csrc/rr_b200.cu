@@ -209,6 +209,7 @@ struct StepArgs {
   int K;
   unsigned vec;  // bit 0 observations, 1 rewards, 2 done: the buffer's rows can be written with 128-bit stores;
                  // bit 3: the action buffer is 4-byte aligned (one 32-bit load per env when A == 4)
+  int block0;    // first block of this launch's env range (sub-batch launches, rr_set_pipeline); 0 for a whole batch
 };
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -223,7 +224,7 @@ template <class L, typename OutT>
 __global__ void __launch_bounds__(L::kMaxBlock, 1) k_step(const __grid_constant__ Consts k, const __grid_constant__ StepArgs a) {
   using E = typename L::E;
   constexpr int R = E::R;
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = ((int64_t)a.block0 + blockIdx.x) * blockDim.x + threadIdx.x;
   const bool live = i < a.N;
   double st[RR_NUM_STATS];
 #pragma unroll
@@ -233,7 +234,9 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_step(const __grid_constant_
 #endif
   E e;
   double cold[E::kColdDoubles];
+  frame_barrier_init();  // (ordered before the first frame by the barrier inside stage_trig_table)
   e.trig = stage_trig_table();
+  FrameSync fs;
 #ifdef RR_DEBUG_COUNT
   e.dbg[0] = e.dbg[1] = e.dbg[2] = e.dbg[3] = 0;
 #endif
@@ -281,7 +284,7 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_step(const __grid_constant_
       }
     }
     StepOut o;
-    sim_step(e, k, cmd, n_cmd, o, live && !bad_action);  // (every thread calls it: block-wide barriers inside)
+    sim_step(e, k, cmd, n_cmd, o, live && !bad_action, fs);  // (every thread calls it: block-wide barriers inside)
     if (bad_action) { o.step_err = RR_ERR_BAD_ACTION; e.err |= RR_ERR_BAD_ACTION; }
     int done_flag = 0;
     if (live) {
@@ -340,6 +343,11 @@ __global__ void __launch_bounds__(L::kMaxBlock, 1) k_step(const __grid_constant_
 #endif
 #ifdef RR_DEBUG_COUNT
   last_naughty = (int)((min(e.dbg[0], 32767u) << 16) | min(e.dbg[2], 65535u));  // slow passes | precise ball-robot tests
+#endif
+#if defined(RR_DEBUG_COUNT) && defined(RR_DEBUG_CLOCK)
+  // diagnostics build: elapsed cycles >> 12 | warp left the frame barrier | slow resolve passes of this env
+  last_naughty = (int)(min((unsigned)((clock64() - dbg_t0) >> 12), 16383u) | (fs.detached ? 1u << 14 : 0u) |
+                       (min(e.dbg[0], 65535u) << 15));
 #endif
   if (live) {
     st[RR_STAT_REPLAYS] = e.mm(kMReplays);
@@ -505,9 +513,26 @@ struct rr_sim {
   cudaStream_t copy_stream = nullptr;  // rr_step_host: results of one chunk of steps travel while the next chunk runs
   cudaEvent_t chunk_done[4] = {nullptr, nullptr, nullptr, nullptr};
   int64_t launches = 0;
+  // sub-batch pipeline (rr_set_pipeline): the batch's blocks in `pipe` contiguous groups, each stepped by its own kernel
+  // on its own stream, so that a group whose slowest env holds it back delays only its own next launch
+  int pipe = 1;
+  std::vector<cudaStream_t> sub;
+  std::vector<cudaEvent_t> sub_done;    // recorded behind a group's latest kernel
+  cudaEvent_t pipe_entry = nullptr;     // recorded on the caller's stream at every rr_step: what the groups wait for
+  bool pipe_pending = false;            // sub-stream work that the caller's stream has not been joined with yet
+  void *flush_buf = nullptr;            // rr_set_flush_buffer: written before every k_step launch (benchmark hygiene)
+  size_t flush_bytes = 0;
+  // rr_step_host_begin / _end: up to RR_HOST_TICKETS calls in flight, each with its own action staging and completion event
+  void *d_act2[RR_HOST_TICKETS] = {};
+  size_t cap_act2[RR_HOST_TICKETS] = {};
+  cudaEvent_t ticket_done[RR_HOST_TICKETS] = {};
+  cudaStream_t ticket_stream[2] = {nullptr, nullptr};  // submission, collection
+  int next_ticket = 0;
   int host_chunks = 0;        // RR_HOST_CHUNKS at rr_create (0 = per-preset default)
   bool host_zero_copy = true; // RR_HOST_ZEROCOPY=0 at rr_create forces the staged path
 };
+
+static void pipeline_free(rr_sim *s);
 
 // Entry points run on the handle's device and leave the caller's current device as they found it.
 struct DeviceGuard {
@@ -664,6 +689,13 @@ int rr_destroy(rr_sim *s) {
   if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
   for (cudaEvent_t e : s->chunk_done)
     if (e) cudaEventDestroy(e);
+  pipeline_free(s);
+  for (int t = 0; t < RR_HOST_TICKETS; t++) {
+    cudaFree(s->d_act2[t]);
+    if (s->ticket_done[t]) cudaEventDestroy(s->ticket_done[t]);
+  }
+  for (cudaStream_t t : s->ticket_stream)
+    if (t) cudaStreamDestroy(t);
   delete s;
   return RR_OK;
 }
@@ -755,10 +787,61 @@ int rr_selftest(int device, int which, int64_t n, uint64_t seed, int64_t *out2) 
   return RR_OK;
 }
 
+// Make `st` wait for everything the sub-batch streams have been given (no host blocking).  Every entry point that reads
+// or writes the state on the caller's stream calls this first, so only consecutive rr_step calls overlap.
+static int join_into(rr_sim *s, cudaStream_t st) {
+  if (!s->pipe_pending) return RR_OK;
+  for (cudaEvent_t e : s->sub_done) CK(cudaStreamWaitEvent(st, e, 0));
+  s->pipe_pending = false;
+  return RR_OK;
+}
+
+static void pipeline_free(rr_sim *s) {
+  for (cudaStream_t t : s->sub) cudaStreamDestroy(t);
+  for (cudaEvent_t e : s->sub_done) cudaEventDestroy(e);
+  if (s->pipe_entry) cudaEventDestroy(s->pipe_entry);
+  s->sub.clear(); s->sub_done.clear(); s->pipe_entry = nullptr; s->pipe = 1; s->pipe_pending = false;
+}
+
+int rr_set_pipeline(rr_sim *s, int32_t sub_batches) {
+  if (!s) return fail(RR_E_INVALID, "null handle");
+  if (sub_batches < 1 || sub_batches > 128) return fail(RR_E_INVALID, "sub_batches must be in [1, 128]");
+  ON_DEVICE(s->device);
+  CK(cudaDeviceSynchronize());
+  pipeline_free(s);
+  if (sub_batches == 1) return RR_OK;
+  CK(cudaEventCreateWithFlags(&s->pipe_entry, cudaEventDisableTiming));
+  for (int j = 0; j < sub_batches; j++) {
+    cudaStream_t t; cudaEvent_t e;
+    CK(cudaStreamCreateWithFlags(&t, cudaStreamNonBlocking));
+    s->sub.push_back(t);
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    s->sub_done.push_back(e);
+  }
+  s->pipe = sub_batches;
+  return RR_OK;
+}
+
+int rr_set_flush_buffer(rr_sim *s, void *buf_dev, int64_t bytes) {
+  if (!s || bytes < 0) return fail(RR_E_INVALID, "bad arguments");
+  ON_DEVICE(s->device);
+  CK(cudaDeviceSynchronize());
+  s->flush_buf = bytes > 0 ? buf_dev : nullptr;
+  s->flush_bytes = s->flush_buf ? (size_t)bytes : 0;
+  return RR_OK;
+}
+
+int rr_join(rr_sim *s, void *stream) {
+  if (!s) return fail(RR_E_INVALID, "null handle");
+  ON_DEVICE(s->device);
+  return join_into(s, (cudaStream_t)stream);
+}
+
 int rr_reset(rr_sim *s, const uint8_t *mask_dev, void *stream) {
   if (!s) return fail(RR_E_INVALID, "null handle");
   ON_DEVICE(s->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (int jr = join_into(s, st)) return jr;
   LAUNCH_PRESET(s, st, (k_reset<L>), s->k, s->sf, s->si, s->N, mask_dev);
   s->launches++;
   CK(cudaGetLastError());
@@ -769,6 +852,7 @@ int rr_reset_fixed(rr_sim *s, const uint8_t *mask_dev, int32_t as_constructed, v
   if (!s) return fail(RR_E_INVALID, "null handle");
   ON_DEVICE(s->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (int jr = join_into(s, st)) return jr;
   LAUNCH_PRESET(s, st, (k_reset_fixed<L>), s->k, s->sf, s->si, s->N, mask_dev, s->start, (int)as_constructed);
   s->launches++;
   CK(cudaGetLastError());
@@ -810,6 +894,7 @@ int rr_observe(rr_sim *s, void *obs_h, void *obs_g, void *stream) {
   if (rr_obs_dim(s) == 0) return RR_OK;
   ON_DEVICE(s->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (int jr = join_into(s, st)) return jr;
   if (s->cfg.out_f64)
     LAUNCH_PRESET(s, st, (k_observe<L, double>), s->k, s->sf, s->si, s->N, obs_h, obs_g);
   else
@@ -829,6 +914,7 @@ int rr_observe_entity(rr_sim *s, int32_t robot, int32_t ball, const int32_t *bal
   if (!ball_dev && ball >= s->B) return fail(RR_E_INVALID, "ball index out of range");
   ON_DEVICE(s->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (int jr = join_into(s, st)) return jr;
   if (s->cfg.out_f64)
     LAUNCH_PRESET(s, st, (k_observe_entity<L, double>), s->k, s->sf, s->si, s->N, (int)robot, (int)ball, ball_dev, obs);
   else
@@ -849,6 +935,7 @@ int rr_assign_balls(rr_sim *s, const int32_t *robots_host, int32_t n_robots, int
   }
   ON_DEVICE(s->device);
   cudaStream_t st = (cudaStream_t)stream;
+  if (int jr = join_into(s, st)) return jr;
   LAUNCH_PRESET(s, st, (k_assign_balls<L>), s->k, s->sf, s->si, s->N, rl, assign_dev);
   s->launches++;
   CK(cudaGetLastError());
@@ -885,12 +972,46 @@ int rr_step(rr_sim *s, const void *actions, int32_t n_actions, int32_t k_steps, 
   if (rows16(rew, s->N * 2 * osz)) vec |= 2u;
   if (rows16(done, (size_t)s->N)) vec |= 4u;
   if ((((uintptr_t)actions) & 3u) == 0) vec |= 8u;
-  StepArgs a{s->sf, s->si, s->stats, actions, obs_h, obs_g, rew, done, s->N, k_steps, vec};
-  if (s->cfg.out_f64)
-    LAUNCH_PRESET(s, st, (k_step<L, double>), k, a);
-  else
-    LAUNCH_PRESET(s, st, (k_step<L, float>), k, a);
-  s->launches++;
+  StepArgs a{s->sf, s->si, s->stats, actions, obs_h, obs_g, rew, done, s->N, k_steps, vec, 0};
+  const bool game = s->cfg.preset == RR_PRESET_GAME, goals = s->cfg.goal_scoring != 0, f64 = s->cfg.out_f64 != 0;
+  auto launch = [&](cudaStream_t on, int block0, int nblocks, int blk) {
+    a.block0 = block0;
+#define RR_STEP_CASE(LTYPE)                                                                                  \
+    do {                                                                                                     \
+      if (f64) k_step<LTYPE, double><<<(unsigned)nblocks, blk, LTYPE::smem_bytes(blk), on>>>(k, a);          \
+      else k_step<LTYPE, float><<<(unsigned)nblocks, blk, LTYPE::smem_bytes(blk), on>>>(k, a);               \
+    } while (0)
+    if (game && !goals) RR_STEP_CASE(LGame);
+    else if (!game && !goals) RR_STEP_CASE(LTrain);
+    else if (game) RR_STEP_CASE(LGameGoals);
+    else RR_STEP_CASE(LTrainGoals);
+#undef RR_STEP_CASE
+  };
+  const int blk = pick_block(s->N, s->sms, game ? LGame::kMaxBlock : LTrain::kMaxBlock);
+  const int nb = (int)((s->N + blk - 1) / blk);
+  const int groups = s->pipe < nb ? s->pipe : nb;
+  if (groups <= 1) {
+    if (int jr = join_into(s, st)) return jr;
+    if (s->flush_buf) CK(cudaMemsetAsync(s->flush_buf, (int)(s->launches & 0xff), s->flush_bytes, st));
+    launch(st, 0, nb, blk);
+    s->launches++;
+  } else {
+    // Sub-batch pipeline: the groups wait for what the caller's stream holds so far (the actions, earlier resets, ...)
+    // and for their own previous launch (stream order); the caller's stream does NOT wait for them (rr_join).
+    CK(cudaEventRecord(s->pipe_entry, st));
+    for (int j = 0; j < groups; j++) {
+      const int b0 = (int)((int64_t)nb * j / groups), b1 = (int)((int64_t)nb * (j + 1) / groups);
+      CK(cudaStreamWaitEvent(s->sub[j], s->pipe_entry, 0));
+      if (s->flush_buf) {  // this group's share of the flush, in front of its launch
+        const size_t f0 = s->flush_bytes / groups * j, f1 = j + 1 == groups ? s->flush_bytes : s->flush_bytes / groups * (j + 1);
+        CK(cudaMemsetAsync((char *)s->flush_buf + f0, (int)(s->launches & 0xff), f1 - f0, s->sub[j]));
+      }
+      launch(s->sub[j], b0, b1 - b0, blk);
+      CK(cudaEventRecord(s->sub_done[j], s->sub[j]));
+      s->launches++;
+    }
+    s->pipe_pending = true;
+  }
   CK(cudaGetLastError());
   return RR_OK;
 }
@@ -934,6 +1055,7 @@ int rr_step_host(rr_sim *s, const void *actions, int32_t n_actions, int32_t k_st
     if (all_pinned) {
       rc = rr_step(s, s->d_act, n_actions, k_steps, obs_b ? a_oh : nullptr, obs_b ? a_og : nullptr, a_rw, (uint8_t *)a_dn, stream);
       if (rc) return rc;
+      if (int jr = join_into(s, st)) return jr;
       CK(cudaStreamSynchronize(st));
       return RR_OK;
     }
@@ -966,6 +1088,7 @@ int rr_step_host(rr_sim *s, const void *actions, int32_t n_actions, int32_t k_st
                  obs_g ? (char *)s->d_obs_g + r0 * obs_row : nullptr, rew ? (char *)s->d_rew + r0 * rew_row : nullptr,
                  done ? s->d_done + r0 * done_row : nullptr, stream);
     if (rc) return rc;
+    if (int jr = join_into(s, st)) return jr;
     CK(cudaEventRecord(s->chunk_done[c], st));
     CK(cudaStreamWaitEvent(s->copy_stream, s->chunk_done[c], 0));
     cudaStream_t cs = s->copy_stream;
@@ -977,6 +1100,54 @@ int rr_step_host(rr_sim *s, const void *actions, int32_t n_actions, int32_t k_st
   }
   CK(cudaStreamSynchronize(s->copy_stream));
   CK(cudaStreamSynchronize(st));
+  return RR_OK;
+}
+
+// Several host-buffer calls in flight.  rr_step_host_begin enqueues one call (actions copied from host memory, result rows
+// written by the kernels straight into the caller's PINNED buffers) and returns a ticket at once; rr_step_host_end blocks
+// until that call's results are in host memory.  With a sub-batch pipeline (rr_set_pipeline) the groups of call n + 1
+// start as soon as their own group of call n has finished, while the host still waits for, or consumes, call n.
+int rr_step_host_begin(rr_sim *s, const void *actions, int32_t n_actions, int32_t k_steps, void *obs_h, void *obs_g, void *rew,
+                       uint8_t *done, int32_t *ticket) {
+  if (!s || !ticket) return fail(RR_E_INVALID, "null argument");
+  int rc = check_actions(s, n_actions, k_steps);
+  if (rc) return rc;
+  if (n_actions > 0 && !actions) return fail(RR_E_INVALID, "actions is null");
+  ON_DEVICE(s->device);
+  const size_t osz = s->cfg.out_f64 ? 8 : 4;
+  const size_t rows = (size_t)k_steps * (size_t)s->N;
+  const size_t act_b = rows * n_actions * (s->cfg.discrete ? 1 : 4);
+  const size_t obs_b = rows * rr_obs_dim(s) * osz;
+  void *a_oh = pinned_alias(obs_h), *a_og = pinned_alias(obs_g), *a_rw = pinned_alias(rew), *a_dn = pinned_alias(done);
+  if ((obs_h && obs_b && !a_oh) || (obs_g && obs_b && !a_og) || (rew && !a_rw) || (done && !a_dn))
+    return fail(RR_E_INVALID, "rr_step_host_begin needs pinned (page-locked, mapped) result buffers; use rr_step_host");
+  if (!s->ticket_stream[0]) {
+    CK(cudaStreamCreateWithFlags(&s->ticket_stream[0], cudaStreamNonBlocking));  // submission: action copies, entry events
+    CK(cudaStreamCreateWithFlags(&s->ticket_stream[1], cudaStreamNonBlocking));  // collection: waits for the groups
+    for (cudaEvent_t &e : s->ticket_done) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  const int t = s->next_ticket;
+  s->next_ticket = (t + 1) % RR_HOST_TICKETS;
+  CK(cudaEventSynchronize(s->ticket_done[t]));  // the call that used this slot last (no-op if never recorded)
+  if ((rc = ensure(&s->d_act2[t], &s->cap_act2[t], act_b ? act_b : 1))) return rc;
+  cudaStream_t sub_st = s->ticket_stream[0], col = s->ticket_stream[1];
+  if (act_b) CK(cudaMemcpyAsync(s->d_act2[t], actions, act_b, cudaMemcpyHostToDevice, sub_st));
+  rc = rr_step(s, s->d_act2[t], n_actions, k_steps, obs_b ? a_oh : nullptr, obs_b ? a_og : nullptr, a_rw, (uint8_t *)a_dn, sub_st);
+  if (rc) return rc;
+  if (s->pipe_pending) {  // the groups of THIS call (their latest events); the submission stream is not held back
+    for (cudaEvent_t e : s->sub_done) CK(cudaStreamWaitEvent(col, e, 0));
+    CK(cudaEventRecord(s->ticket_done[t], col));
+  } else {
+    CK(cudaEventRecord(s->ticket_done[t], sub_st));
+  }
+  *ticket = t;
+  return RR_OK;
+}
+
+int rr_step_host_end(rr_sim *s, int32_t ticket) {
+  if (!s || ticket < 0 || ticket >= RR_HOST_TICKETS || !s->ticket_done[ticket]) return fail(RR_E_INVALID, "bad ticket");
+  ON_DEVICE(s->device);
+  CK(cudaEventSynchronize(s->ticket_done[ticket]));
   return RR_OK;
 }
 
@@ -1131,6 +1302,7 @@ int rr_stats_device_ptr(rr_sim *s, double **p) {
 int rr_clear_stats(rr_sim *s, void *stream) {
   if (!s) return fail(RR_E_INVALID, "null handle");
   ON_DEVICE(s->device);
+  if (int jr = join_into(s, (cudaStream_t)stream)) return jr;
   CK(cudaMemsetAsync(s->stats, 0, sizeof(double) * RR_NUM_STATS, (cudaStream_t)stream));
   return RR_OK;
 }

@@ -26,7 +26,7 @@ class RoboRugbyVecEnv:
     def __init__(self, env_id="RoboRugbySimpleDuel-v2", num_envs=4096, preset="GAME", device="cuda:0", seed=0,
                  env_offset=0, time_limit=True, auto_reset=True, out_dtype=torch.float32, strict_reset=True,
                  n_actions=None, observer=None, reward_mask=None, reward_order=None, reward_mixins=None, flags=0,
-                 goal_scoring=False):
+                 goal_scoring=False, pipeline=1):
         if env_id not in ENV_IDS:
             raise ValueError(f"unknown env id {env_id!r}; expected one of {ENV_IDS}")
         if not torch.cuda.is_available():
@@ -75,6 +75,29 @@ class RoboRugbyVecEnv:
         self.stats = torch.zeros(_lib.NUM_STATS, dtype=torch.float64, device=self.device)
         _lib.check(self.lib.rr_set_stats_buffer(h, self.stats.data_ptr()))
         self._bufs = {}
+        self.pipeline = 1
+        if pipeline and int(pipeline) > 1:
+            self.set_pipeline(pipeline)
+
+    # ------------------------------------------------------------------ sub-batch pipeline
+    def set_pipeline(self, sub_batches):
+        """Step the batch as `sub_batches` independent groups of blocks on the handle's own streams (rr_set_pipeline):
+        a group held back by its slowest env delays only its own next launch.  With sub_batches > 1, step_k(..., join=False)
+        returns without making the current stream wait for the groups, so back-to-back calls overlap; call join() before
+        reading results.  Every other method joins by itself.  Results do not depend on the setting."""
+        _lib.check(self.lib.rr_set_pipeline(self._h, int(sub_batches)))
+        self.pipeline = int(sub_batches)
+
+    def set_flush_buffer(self, buf):
+        """Benchmark hygiene: `buf` (a CUDA uint8 tensor larger than the L2, or None) is overwritten in front of every step
+        launch on the launching stream (rr_set_flush_buffer)."""
+        self._flush = buf
+        _lib.check(self.lib.rr_set_flush_buffer(self._h, buf.data_ptr() if buf is not None else None,
+                                                buf.numel() if buf is not None else 0))
+
+    def join(self):
+        """Make the current stream wait (on the device) for every group's outstanding launches."""
+        _lib.check(self.lib.rr_join(self._h, self._stream()))
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
@@ -187,9 +210,11 @@ class RoboRugbyVecEnv:
         info = {"obs_grumpy": obs_g[0], "reward_grumpy": rew[0, :, 1]}
         return obs_h[0], rew[0, :, 0], done[0].bool(), info
 
-    def step_k(self, actions, k):
-        """k fused env-steps in ONE kernel launch.  actions [k, N, A]; returns obs_h [k,N,D], obs_g,
-        rew [k,N,2], done [k,N] (uint8).  Envs that finish are reset inside the launch (auto_reset)."""
+    def step_k(self, actions, k, join=True):
+        """k fused env-steps in ONE kernel launch (one per group with a sub-batch pipeline).  actions [k, N, A]; returns
+        obs_h [k,N,D], obs_g, rew [k,N,2], done [k,N] (uint8).  Envs that finish are reset inside the launch (auto_reset).
+        join=False (pipeline > 1 only): do not make the current stream wait for the launches; the caller joins later and
+        must not touch `actions` or the returned buffers before that."""
         actions = self._check_actions(actions, k)
         A = actions.shape[2]
         b = self._out(k)
@@ -198,6 +223,11 @@ class RoboRugbyVecEnv:
                                     b["obs_h"].data_ptr() if has_obs else None,
                                     b["obs_g"].data_ptr() if has_obs else None,
                                     b["rew"].data_ptr(), b["done"].data_ptr(), self._stream()))
+        if self.pipeline > 1:
+            if join:
+                self.join()
+            else:
+                self._inflight_actions = actions   # keep the buffer alive until the groups have read it
         return b["obs_h"][..., :self.obs_dim], b["obs_g"][..., :self.obs_dim], b["rew"], b["done"]
 
     def step_host(self, actions_host, k, out=None):
@@ -220,6 +250,34 @@ class RoboRugbyVecEnv:
                                          out["obs_g"].data_ptr() if has_obs and out.get("obs_g") is not None else None,
                                          out["rew"].data_ptr(), out["done"].data_ptr(), self._stream()))
         return out
+
+    def step_host_begin(self, actions_host, k, slot):
+        """rr_step_host_begin: enqueue k fused steps with HOST buffers and return a ticket at once.  `slot` picks one of the
+        caller's sets of pinned result buffers (one per call kept in flight, at most 4): begin calls n + 1, n + 2 on other
+        slots before ending call n."""
+        want = torch.uint8 if self.discrete else torch.float32
+        assert actions_host.device.type == "cpu" and actions_host.dtype == want and actions_host.is_contiguous()
+        A = actions_host.shape[-1] if actions_host.dim() == 3 else 1
+        key = ("host2", k, int(slot))
+        if key not in self._bufs:
+            N, D = self.num_envs, max(self.obs_dim, 1)
+            mk = lambda *s, dt=self.out_dtype: torch.empty(*s, dtype=dt).pin_memory()
+            self._bufs[key] = dict(obs_h=mk(k, N, D), obs_g=mk(k, N, D), rew=mk(k, N, 2), done=mk(k, N, dt=torch.uint8))
+        out = self._bufs[key]
+        has_obs = self.obs_dim > 0
+        ticket = C.c_int32(-1)
+        _lib.check(self.lib.rr_step_host_begin(self._h, actions_host.data_ptr(), A, k,
+                                               out["obs_h"].data_ptr() if has_obs else None,
+                                               out["obs_g"].data_ptr() if has_obs else None,
+                                               out["rew"].data_ptr(), out["done"].data_ptr(), C.byref(ticket)))
+        self._tickets = getattr(self, "_tickets", {})
+        self._tickets[ticket.value] = (out, actions_host)
+        return ticket.value
+
+    def step_host_end(self, ticket):
+        """Block until the call behind `ticket` has delivered its results; returns its pinned result buffers."""
+        _lib.check(self.lib.rr_step_host_end(self._h, int(ticket)))
+        return self._tickets[int(ticket)][0]
 
     # ------------------------------------------------------------------ introspection / parity
     def get_state(self):
@@ -266,10 +324,12 @@ class RoboRugbyVecEnv:
     # ------------------------------------------------------------------ statistics
     def get_stats(self):
         """Episode statistics of THIS shard since the last clear_stats(), as a dict."""
+        self.join()
         v = self.stats.cpu().tolist()
         return dict(zip(_lib.STAT_NAMES, v))
 
     def clear_stats(self):
+        self.join()
         self.stats.zero_()
 
     def reduce_stats(self, group=None):
@@ -277,6 +337,7 @@ class RoboRugbyVecEnv:
         NVLink/NVSwitch; the env shards themselves never exchange state).  Returns a dict of the
         GLOBAL statistics; the local vector is left untouched."""
         from .stats import allreduce_stats
+        self.join()
         return allreduce_stats(self.stats, group)
 
     @property

@@ -90,7 +90,7 @@ static unsigned step_t(const Consts &k, double *rob, double *rhist, int32_t *rfl
       cmd |= pack_thrust(r, (int)rint((double)(float)actions[2 * r]), (int)rint((double)(float)actions[2 * r + 1]));
   }
   StepOut o;
-  sim_step(e, k, cmd, n_cmd, o, true);
+  { FrameSync fs_; sim_step(e, k, cmd, n_cmd, o, true, fs_); }
   g_last_replays = e.mm(kMReplays);
   g_last_whole = e.mm(kMFrames);
   g_last_stuck = e.mm(kMStuckReplays);
@@ -122,7 +122,7 @@ static unsigned step_k_t(const Consts &k, double *rob, double *rhist, int32_t *r
       cmd |= pack_thrust(r, l, rt);
     }
     StepOut o;
-    sim_step(e, k, cmd, n_actions, o, true);
+    { FrameSync fs_; sim_step(e, k, cmd, n_actions, o, true, fs_); }
     rew_out[2 * s] = o.rew_h; rew_out[2 * s + 1] = o.rew_g;
     errs |= o.step_err;
     if (o.step_err) break;
@@ -161,7 +161,7 @@ static unsigned goal_rollout_t(const Consts &k, double *rob, double *rhist, int3
         cmd |= pack_thrust(r, (int)rint((double)(float)a[2 * r]), (int)rint((double)(float)a[2 * r + 1]));
     }
     StepOut o;
-    sim_step(e, k, cmd, n_cmd, o, true);
+    { FrameSync fs_; sim_step(e, k, cmd, n_cmd, o, true, fs_); }
     errs |= o.step_err;
     if (o.step_err) break;
     rew_out[2 * s] = o.rew_h; rew_out[2 * s + 1] = o.rew_g;

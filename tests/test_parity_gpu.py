@@ -791,3 +791,77 @@ def test_gpu_error_rate_of_random_rollouts_is_bounded():
     errs = env.error_mask()
     assert (errs != 0).sum() <= st["errors"]     # sticky per-env masks: at most one per error step
     env.close()
+
+
+@pytest.mark.parametrize("preset,groups", [("GAME", 7), ("GAME", 128), ("TRAIN", 5)])
+def test_gpu_sub_batch_pipeline_is_bit_identical(preset, groups):
+    """rr_set_pipeline: the batch stepped as independent groups of blocks on the handle's own streams, consecutive calls
+    issued back to back without a join in between, equals one stream-ordered launch per call bit for bit (outputs of
+    every call, final state, error masks; statistics up to the order of the atomic additions).  Entry points that read or
+    write the state join by themselves (reset / observe between pipelined calls)."""
+    N, K = 20000, 6
+    g = torch.Generator().manual_seed(9)
+    mk = lambda **kw: _venv(V2, N, preset, seed=21, out_dtype=torch.float32, time_limit=True, auto_reset=True, **kw)
+    a, b = mk(), mk(pipeline=groups)
+    assert b.pipeline == groups
+    for env in (a, b):   # episode ends (auto-reset) inside the launches
+        st = env.get_state(); st["step"][:] = env.max_episode_steps - 1 - (np.arange(N) % (3 * K)); env.set_state(st)
+    acts = [torch.randint(0, 8, (K, N, a.num_robots), generator=g, dtype=torch.uint8).cuda() for _ in range(4)]
+    outs_a, outs_b = [], []
+    for c in range(4):
+        outs_a.append([x.clone() for x in a.step_k(acts[c], K)])
+        ob = b.step_k(acts[c], K, join=False)   # no join between the calls: groups of call c + 1 overlap call c
+        if c == 1:   # an entry point on the caller's stream in the middle: joins, resets a few envs, observes
+            mask = torch.zeros(N, dtype=torch.uint8); mask[::97] = 1
+            ra = a.reset(mask.cuda()); rb = b.reset(mask.cuda())
+            assert torch.equal(ra, rb)
+        if c == 3:
+            b.join()
+            outs_b.append([x.clone() for x in ob])
+    torch.cuda.synchronize()
+    same = lambda x, y: np.array_equal(x.cpu().numpy(), y.cpu().numpy(), equal_nan=True)
+    assert all(same(x, y) for x, y in zip(outs_a[3], outs_b[0]))
+    sa, sb = a.get_state(), b.get_state()
+    for k in STATE_KEYS:
+        assert np.array_equal(sa[k], sb[k]), k
+    assert np.array_equal(a.error_mask(), b.error_mask())
+    ta, tb = a.get_stats(), b.get_stats()
+    assert ta["episodes"] == tb["episodes"] > 0 and ta["steps"] == tb["steps"] == 4 * K * N
+    assert ta["naughty"] == tb["naughty"]
+    assert b.launch_count - 1 > a.launch_count - 1   # one kernel per group and call
+    b.set_pipeline(1)   # back to one launch per call, same handle
+    assert all(same(x, y) for x, y in zip(a.step_k(acts[0], K), b.step_k(acts[0], K)))
+
+
+def test_gpu_step_host_begin_end_matches_step_host():
+    """rr_step_host_begin / _end with three calls in flight (pinned result buffers, sub-batch pipeline on) delivers the
+    rows of rr_step_host, call by call, and leaves the same state."""
+    N, K, calls = 6000, 5, 7
+    g = torch.Generator().manual_seed(12)
+    mk = lambda **kw: _venv(V2, N, "GAME", seed=8, out_dtype=torch.float32, time_limit=True, auto_reset=True, **kw)
+    a, b = mk(), mk(pipeline=6)
+    for env in (a, b):
+        st = env.get_state(); st["step"][:] = env.max_episode_steps - 1 - (np.arange(N) % (2 * K)); env.set_state(st)
+    acts = [torch.randint(0, 8, (K, N, a.num_robots), generator=g, dtype=torch.uint8).pin_memory() for _ in range(calls)]
+    want = []
+    for c in range(calls):
+        o = a.step_host(acts[c], K)
+        want.append({k: v.clone() for k, v in o.items()})
+    depth = 3
+    pending = [b.step_host_begin(acts[c], K, c % depth) for c in range(depth - 1)]
+    for c in range(calls):
+        nx = c + depth - 1
+        if nx < calls:
+            pending.append(b.step_host_begin(acts[nx], K, nx % depth))
+        o = b.step_host_end(pending.pop(0))
+        for k in ("obs_h", "obs_g", "rew", "done"):
+            assert np.array_equal(o[k].numpy(), want[c][k].numpy(), equal_nan=True), (c, k)
+    for k in STATE_KEYS:
+        assert np.array_equal(a.get_state()[k], b.get_state()[k]), k
+    # pageable result buffers are refused (the kernels write into them directly)
+    from roborugby_b200 import _lib
+    import ctypes as C
+    pag = torch.empty(K, N, 2)
+    t = C.c_int32(-1)
+    rc = b.lib.rr_step_host_begin(b._h, acts[0].data_ptr(), a.num_robots, K, None, None, pag.data_ptr(), None, C.byref(t))
+    assert rc != 0 and b"pinned" in b.lib.rr_last_error()
