@@ -31,12 +31,24 @@ namespace rr {
 // wave.  The hot per-env doubles (robot rects) live in shared memory, [field][thread] with the block
 // size as stride: GAME 56 doubles x 448 threads = 196 KB; the cold ones (balls, history slots) in a
 // per-thread local array.
-template <int NH, int NG, int NP, int NN, bool GOALS = false>
+template <int NH, int NG, int NP, int NN, bool GOALS = false, int MAXB = 0>
 struct Launch {
   static constexpr int R = NH + NG, B = NP + NN;
-  using E = Env<NH, NG, NP, NN, GOALS>;
+  using E = Env<NH, NG, NP, NN, GOALS, MAXB>;
   // largest block: bounded by 227 KB of shared memory and by 65 536 registers per SM
-  static constexpr int kMaxBlock = R > 1 ? 448 : 512;
+  // The register file is per SM sub-partition (4 x 16 384 registers): 12 warps = 3 per sub-partition may use 168 registers
+  // per thread, 13 - 16 warps only 128.  GAME: 384 threads x 168 registers beat 448 x 128 by 7.5 % once the sub-batch
+  // pipeline (rr_set_pipeline) made the number of blocks a free parameter (171 blocks on 148 SMs no longer means two waves
+  // of one launch); measured 416 / 384 / 352 / 320 threads: 139.8 / 151.7 / 142.9 / 135.5 M env-steps/s.
+#ifndef RR_MAX_BLOCK_GAME
+#define RR_MAX_BLOCK_GAME 384
+#endif
+#ifndef RR_MAX_BLOCK_TRAIN
+#define RR_MAX_BLOCK_TRAIN 512
+#endif
+  // MAXB != 0: the wide k_step variant (GAME, 448 threads x 128 registers) for a caller that steps a batch of more than
+  // 384 x #SM envs one stream-ordered launch at a time: one wave of 448-thread blocks then beats two waves of 384
+  static constexpr int kMaxBlock = MAXB ? MAXB : (R > 1 ? RR_MAX_BLOCK_GAME : RR_MAX_BLOCK_TRAIN);
   static constexpr int kTrigDoubles = kTrigRows * 4;  // sin/cos tables staged in front of the env fields
   // behind the env fields: one 640-byte staging area per warp, through which a warp's result rows (160 floats of
   // observations, 64 of rewards, 32 done bytes) are turned into full 128-bit stores (warp_store_rows)
@@ -592,6 +604,8 @@ using LGame = Launch<2, 2, 4, 4>;
 using LTrain = Launch<1, 0, 1, 0>;
 using LGameGoals = Launch<2, 2, 4, 4, true>;   // rr_config.goal_scoring = 1
 using LTrainGoals = Launch<1, 0, 1, 0, true>;
+using LGameWide = Launch<2, 2, 4, 4, false, 448>;   // k_step only (see Launch::kMaxBlock)
+using LGameGoalsWide = Launch<2, 2, 4, 4, true, 448>;
 
 // Every kernel uses more than the default 48 KB of dynamic shared memory: opt in once per device (rr_create), not per
 // launch (the attribute call costs more than a K = 1 launch's own CPU time).
@@ -666,6 +680,15 @@ int rr_create(const rr_config *cfg, int64_t n_envs, int device, rr_sim **out) {
     return fail(RR_E_NOMEM, "device allocation failed");
   }
   s->stats = s->own_stats;
+  if (game) {  // the wide k_step variants
+    const int wb = (int)LGameWide::smem_bytes(LGameWide::kMaxBlock);
+    cudaError_t we = cfg->goal_scoring
+        ? (cudaFuncSetAttribute(k_step<LGameGoalsWide, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, wb),
+           cudaFuncSetAttribute(k_step<LGameGoalsWide, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, wb))
+        : (cudaFuncSetAttribute(k_step<LGameWide, float>, cudaFuncAttributeMaxDynamicSharedMemorySize, wb),
+           cudaFuncSetAttribute(k_step<LGameWide, double>, cudaFuncAttributeMaxDynamicSharedMemorySize, wb));
+    if (we != cudaSuccess) { rr_destroy(s); return fail(RR_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(we)); }
+  }
   {
     cudaError_t ae = cfg->goal_scoring ? (game ? opt_in_shared_memory<LGameGoals>() : opt_in_shared_memory<LTrainGoals>())
                                        : (game ? opt_in_shared_memory<LGame>() : opt_in_shared_memory<LTrain>());
@@ -974,6 +997,11 @@ int rr_step(rr_sim *s, const void *actions, int32_t n_actions, int32_t k_steps, 
   if ((((uintptr_t)actions) & 3u) == 0) vec |= 8u;
   StepArgs a{s->sf, s->si, s->stats, actions, obs_h, obs_g, rew, done, s->N, k_steps, vec, 0};
   const bool game = s->cfg.preset == RR_PRESET_GAME, goals = s->cfg.goal_scoring != 0, f64 = s->cfg.out_f64 != 0;
+  // one stream-ordered launch per call over more envs than 384-thread blocks cover in one wave: 448-thread blocks
+  const bool wide = game && s->pipe <= 1 && (s->N + LGame::kMaxBlock - 1) / LGame::kMaxBlock > s->sms &&
+                    LGame::kMaxBlock < LGameWide::kMaxBlock;
+  const int blk = pick_block(s->N, s->sms, wide ? LGameWide::kMaxBlock : (game ? LGame::kMaxBlock : LTrain::kMaxBlock));
+  const int nb = (int)((s->N + blk - 1) / blk);
   auto launch = [&](cudaStream_t on, int block0, int nblocks, int blk) {
     a.block0 = block0;
 #define RR_STEP_CASE(LTYPE)                                                                                  \
@@ -981,14 +1009,12 @@ int rr_step(rr_sim *s, const void *actions, int32_t n_actions, int32_t k_steps, 
       if (f64) k_step<LTYPE, double><<<(unsigned)nblocks, blk, LTYPE::smem_bytes(blk), on>>>(k, a);          \
       else k_step<LTYPE, float><<<(unsigned)nblocks, blk, LTYPE::smem_bytes(blk), on>>>(k, a);               \
     } while (0)
-    if (game && !goals) RR_STEP_CASE(LGame);
+    if (game && !goals) { if (wide) RR_STEP_CASE(LGameWide); else RR_STEP_CASE(LGame); }
     else if (!game && !goals) RR_STEP_CASE(LTrain);
-    else if (game) RR_STEP_CASE(LGameGoals);
+    else if (game) { if (wide) RR_STEP_CASE(LGameGoalsWide); else RR_STEP_CASE(LGameGoals); }
     else RR_STEP_CASE(LTrainGoals);
 #undef RR_STEP_CASE
   };
-  const int blk = pick_block(s->N, s->sms, game ? LGame::kMaxBlock : LTrain::kMaxBlock);
-  const int nb = (int)((s->N + blk - 1) / blk);
   const int groups = s->pipe < nb ? s->pipe : nb;
   if (groups <= 1) {
     if (int jr = join_into(s, st)) return jr;

@@ -467,8 +467,9 @@ def test_gpu_config1_simple_v0_4096_envs_per_step_parity(oracle):
 BENCH_RATCHET = {True: (2, 0.80), False: (2, 0.80)}
 
 
-@pytest.mark.parametrize("strict", [True, False], ids=["strict_reset", "relaxed_reset"])
-def test_gpu_bench_configuration_matches_oracle(oracle, strict):
+@pytest.mark.parametrize("strict,pipeline", [(True, 128), (True, 1), (False, 1)],
+                         ids=["strict_reset-pipeline128", "strict_reset-single_launch", "relaxed_reset-single_launch"])
+def test_gpu_bench_configuration_matches_oracle(oracle, strict, pipeline):
     """BASELINE.json configs[2] exactly as bench.py runs it: RoboRugbySimpleDuel-v2, GAME constants, 65 536 envs, ONE
     launch of 32 fused env-steps, float32 outputs (the k_step<Launch<2,2,4,4>, float> instantiation), auto-reset inside
     the launch, episode phases desynchronised with bench.py's formula.  1 024 sampled envs are replayed by the oracle
@@ -476,10 +477,14 @@ def test_gpu_bench_configuration_matches_oracle(oracle, strict):
     plus the final state.  Integers exact; fp64 state within 1e-9; fp32 outputs within one fp32 ulp of the cast oracle
     value (bit-equal counts are printed and ratcheted).  An env whose trajectory flipped a contact decision on a
     last-bit difference is counted as diverged (bounded), never skipped silently.  `strict` = the reset placement
-    mode: the reference's own (strict_reset=1, the product default and what bench.py runs) and the relaxed one."""
+    mode: the reference's own (strict_reset=1, the product default and what bench.py runs) and the relaxed one.
+    `pipeline` = 128: bench.py's sub-batch pipeline, i.e. 128 launches of the 384-thread / 168-register k_step over
+    groups of blocks; 1: one launch of the 448-thread / 128-register variant over the whole batch (rr_step picks it for a
+    single launch over more envs than 384-thread blocks cover in one wave)."""
     N, K, seed = 65536, 32, 2026
     env = _venv(V2, N, "GAME", seed=seed, env_offset=0, time_limit=True, auto_reset=True, out_dtype=torch.float32,
-                strict_reset=strict)
+                strict_reset=strict, pipeline=pipeline)
+    assert env.launch_count == 1
     T = env.max_episode_steps
     st = env.get_state()
     st["step"][:] = (np.arange(N) * 7919) % max(T - 1, 1)     # bench.py's desynchronisation
@@ -491,6 +496,7 @@ def test_gpu_bench_configuration_matches_oracle(oracle, strict):
     obs_h, obs_g, rew, done = env.step_k(acts, K)
     assert obs_h.dtype == torch.float32 and rew.dtype == torch.float32
     torch.cuda.synchronize()
+    assert env.launch_count - 1 == (128 if pipeline > 1 else 1)
     fin = env.get_state()
     err = env.error_mask()
     sel = torch.as_tensor(sample, device="cuda")
