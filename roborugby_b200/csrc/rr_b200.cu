@@ -49,6 +49,10 @@ struct Launch {
   // MAXB != 0: the wide k_step variant (GAME, 448 threads x 128 registers) for a caller that steps a batch of more than
   // 384 x #SM envs one stream-ordered launch at a time: one wave of 448-thread blocks then beats two waves of 384
   static constexpr int kMaxBlock = MAXB ? MAXB : (R > 1 ? RR_MAX_BLOCK_GAME : RR_MAX_BLOCK_TRAIN);
+#ifndef RR_STEP_BLOCKS_PER_SM
+#define RR_STEP_BLOCKS_PER_SM 1
+#endif
+  static constexpr int kStepBlocksPerSM = (R > 1 && MAXB == 0) ? RR_STEP_BLOCKS_PER_SM : 1;  // A/B switch (2 x 192 threads: measured slower)
   static constexpr int kTrigDoubles = kTrigRows * 4;  // sin/cos tables staged in front of the env fields
   // behind the env fields: one 640-byte staging area per warp, through which a warp's result rows (160 floats of
   // observations, 64 of rewards, 32 done bytes) are turned into full 128-bit stores (warp_store_rows)
@@ -233,7 +237,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 // The fused multi-step kernel: K env-steps per launch, auto-reset inside.  Padding threads of the
 // last block (i >= N) run the control flow without an env so that the per-frame barrier is uniform.
 template <class L, typename OutT>
-__global__ void __launch_bounds__(L::kMaxBlock, 1) k_step(const __grid_constant__ Consts k, const __grid_constant__ StepArgs a) {
+__global__ void __launch_bounds__(L::kMaxBlock, L::kStepBlocksPerSM) k_step(const __grid_constant__ Consts k, const __grid_constant__ StepArgs a) {
   using E = typename L::E;
   constexpr int R = E::R;
   const int64_t i = ((int64_t)a.block0 + blockIdx.x) * blockDim.x + threadIdx.x;
