@@ -330,6 +330,13 @@ def main():
     h2d = K * n_local * act_bytes
     d2h = K * n_local * (2 * D * 4 + 2 * 4 + 1)
     sampler.stop()
+    clocks = sampler.summary()
+    per_rank_clocks = None
+    if world > 1:  # every rank samples its own GPU: a slower rank is usually a GPU that clocks lower under the fp64 load
+        mine = torch.tensor([float(clocks["sm_mhz"] or 0.0), float(len(clocks["reasons"]))], dtype=torch.float64, device=dev)
+        allc = [torch.zeros(2, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(allc, mine)
+        per_rank_clocks = [float(x[0].item()) for x in allc]
 
     stats = env.reduce_stats()  # the one optional collective: 64-byte all-reduce of episode statistics
     err_envs = int((env.error_mask() != 0).sum())
@@ -338,6 +345,8 @@ def main():
 
     # ---------------- extras: one env-step per launch (env.step()), DQN loop ----------------
     extras = {"per_rank_ms_per_call": per_rank_ms}
+    if per_rank_clocks is not None:
+        extras["per_rank_sm_mhz_median"] = per_rank_clocks
     if not args.no_extras:
         # (a) the same calls one stream-ordered launch at a time (no pipeline): the round-1 definition of `value`
         env.set_pipeline(1)
@@ -404,7 +413,7 @@ def main():
                          "kernel": KERNEL_NAME[args.preset],
                          "secondary": dict(NCU_SECONDARY[args.preset], source=PROFILE_SOURCE[args.preset]),
                          "note": "path is fp64-issue / latency bound, not HBM bound (DESIGN.md §4)"},
-            "clocks": sampler.summary(),
+            "clocks": clocks,
             "episode_stats": {k: stats[k] for k in ("episodes", "mean_return_happy", "mean_return_grumpy", "mean_length",
                                                     "naughty", "errors", "steps")},
             "error_envs": err_envs,
