@@ -300,6 +300,9 @@ __global__ void __launch_bounds__(L::kMaxBlock, L::kStepBlocksPerSM) k_step(cons
       }
     }
     StepOut o;
+#ifdef RR_DEBUG_FRAMES
+    fs.parity = (unsigned)s;  // (RR_DETACH is off in diagnostics builds: the field is free)
+#endif
     sim_step(e, k, cmd, n_cmd, o, live && !bad_action, fs);  // (every thread calls it: block-wide barriers inside)
     if (bad_action) { o.step_err = RR_ERR_BAD_ACTION; e.err |= RR_ERR_BAD_ACTION; }
     int done_flag = 0;
@@ -354,6 +357,17 @@ __global__ void __launch_bounds__(L::kMaxBlock, L::kStepBlocksPerSM) k_step(cons
       }
     }
   }
+#ifdef RR_DEBUG_FRAMES
+  __syncthreads();
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.K >= 8) {
+    const int nw = (int)(blockDim.x >> 5);
+    for (int q = 0; q < a.K * 12 && q < 64 * 12; q++) {
+      printf("FR %d", q);
+      for (int w = 0; w < nw; w++) printf(" %lld:%x", rr_dbg_arrive[q * 16 + w] - rr_dbg_arrive[0], rr_dbg_paths[q * 16 + w]);
+      printf("\n");
+    }
+  }
+#endif
 #ifdef RR_DEBUG_CLOCK
   last_naughty = (int)((clock64() - dbg_t0) >> 10);  // per-thread elapsed kilo-cycles (debug builds only)
 #endif
