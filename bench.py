@@ -39,19 +39,24 @@ ENV_ID = "RoboRugbySimpleDuel-v2"
 ENVS_PER_GPU = 65536
 FUSED = 32
 PIPELINE = 128  # sub-batch groups (rr_set_pipeline): a group held back by its slowest env delays only its own next launch
-# Figures of ONE k_step launch of the bench workload (65 536 envs x 32 steps) from the committed `ncu --set full`
-# capture of the committed kernel (profiles/, see PROFILE_SOURCE): dram__bytes_read.sum + dram__bytes_write.sum
-# (reported as roofline.traffic when the bench runs that exact workload) and the pipe / issue / SM-busy figures that
-# bound the kernel (reported as roofline.secondary; the path is not HBM-bound).
+# Figures from the committed `ncu --set full` captures of the committed kernels (profiles/, see PROFILE_SOURCE).  A bench
+# call is 128 kernel launches over groups of blocks (sub-batch pipeline), which ncu cannot capture as one unit, so the
+# captures are ONE WAVE of the same kernel: GAME 56 832 envs = 148 blocks of 384 threads x 32 steps (`--envs 56832
+# --pipeline 1`), TRAIN 65 536 envs = 147 blocks of 448 threads.  dram__bytes_read.sum + dram__bytes_write.sum is reported
+# as roofline.traffic per bench call (the GAME figure scaled by 65 536 / 56 832 envs); the pipe / issue / stall figures
+# that bound the kernel as roofline.secondary (the path is not HBM-bound).  sm_busy_pipelined = sum of
+# the block times / (148 SMs x time per call) of the pipelined run, instrumented build (profiles/r02_pipeline_block_chains.txt).
 PROFILE_SOURCE = {"GAME": "profiles/r02_k_step_game_by_function.txt", "TRAIN": "profiles/r02_k_step_train_by_function.txt"}
-NCU_TRAFFIC_BYTES = {"GAME": 267.35e6 + 1773.45e6, "TRAIN": 15.57e6 + 114.23e6}
+NCU_TRAFFIC_BYTES = {"GAME": (136.85e6 + 1086.35e6) * 65536 / 56832, "TRAIN": 15.41e6 + 126.62e6}
 NCU_SECONDARY = {
-    "GAME": {"fp64_pipe_pct": 15.5, "issue_slots_busy_pct": 26.3, "warps_active_pct": 21.8, "sm_busy_frac": 0.863,
-             "barrier_stall_per_issue": 3.68, "long_scoreboard_per_issue": 2.72, "threads_per_instruction": 21.0},
-    "TRAIN": {"fp64_pipe_pct": 17.2, "issue_slots_busy_pct": 31.9, "warps_active_pct": 21.8, "sm_busy_frac": 0.887,
-              "barrier_stall_per_issue": 2.60, "long_scoreboard_per_issue": 0.92, "threads_per_instruction": 22.7},
+    "GAME": {"fp64_pipe_pct": 17.8, "issue_slots_busy_pct": 29.0, "warps_active_pct": 18.7, "sm_busy_frac_single_wave": 0.671,
+             "sm_busy_pipelined": 0.944, "barrier_stall_per_issue": 2.45, "long_scoreboard_per_issue": 1.12,
+             "threads_per_instruction": 21.8, "registers_per_thread": 168, "block": 384},
+    "TRAIN": {"fp64_pipe_pct": 18.2, "issue_slots_busy_pct": 33.7, "warps_active_pct": 21.8, "sm_busy_frac_single_wave": 0.878,
+              "barrier_stall_per_issue": 2.01, "long_scoreboard_per_issue": 0.91, "threads_per_instruction": 23.5,
+              "registers_per_thread": 128, "block": 448},
 }
-KERNEL_NAME = {"GAME": "rr::k_step<rr::Launch<2, 2, 4, 4, 0>, float>", "TRAIN": "rr::k_step<rr::Launch<1, 0, 1, 0, 0>, float>"}
+KERNEL_NAME = {"GAME": "rr::k_step<rr::Launch<2, 2, 4, 4, 0, 0>, float>", "TRAIN": "rr::k_step<rr::Launch<1, 0, 1, 0, 0, 0>, float>"}
 # The Python reference itself (unmodified, stub pygame/gym) cannot travel to the GPU box; its own rate, measured in the
 # build container with oracle/time_reference.py (8 cores, one process per core), is recorded beside the port's.
 PY_REFERENCE_NOTE = {"GAME": "Python reference (oracle/time_reference.py, build container, 8 cores): 123 env-steps/s (18.9 per core)",
@@ -408,7 +413,10 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (NCU_TRAFFIC_BYTES[args.preset] if (args.envs, args.fused) == (ENVS_PER_GPU, FUSED)
                                      else None),
-                         "traffic_source": PROFILE_SOURCE[args.preset] + " (dram bytes read + written per launch)",
+                         "traffic_source": PROFILE_SOURCE[args.preset] + " (dram bytes read + written by one wave of the kernel, "
+                                           "scaled to the envs of one bench call)",
+                         "achieved_note": "algorithmic bytes of one bench call / (timed region / calls): the calls overlap "
+                                          "(sub-batch pipeline), so this is the sustained rate, not one launch alone",
                          "algorithmic_bytes_per_launch": bytes_per_launch, "peak_source": peak_src, "bytes_per_env_step": q, "state_bytes": S,
                          "kernel": KERNEL_NAME[args.preset],
                          "secondary": dict(NCU_SECONDARY[args.preset], source=PROFILE_SOURCE[args.preset]),
