@@ -271,7 +271,8 @@ def main():
     env.set_state(st)
 
     env.set_pipeline(args.pipeline)
-    env.set_flush_buffer(flush)
+    if not os.environ.get("RR_BENCH_NO_FLUSH"):
+        env.set_flush_buffer(flush)
     for w in range(args.warmup):
         env.step_k(acts[w % n_sets], K)
     barrier()
