@@ -19,9 +19,11 @@ _SRCS = [os.path.join(_HERE, "rr_emul.cu"), os.path.join(_ROOT, "roborugby_b200"
 
 def build(force=False):
     if force or not os.path.exists(_LIB) or os.path.getmtime(_LIB) < max(os.path.getmtime(p) for p in _SRCS):
+        tmp = f"{_LIB}.{os.getpid()}.tmp"   # (pytest-xdist workers may all find the library stale at once)
         subprocess.check_call([
             "nvcc", "-O2", "-std=c++17", "--fmad=false", "-Wno-deprecated-gpu-targets",
-            "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-builtin", "-shared", "-o", _LIB, _SRCS[0]])
+            "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-builtin", "-shared", "-o", tmp, _SRCS[0]])
+        os.replace(tmp, _LIB)
     return _LIB
 
 
