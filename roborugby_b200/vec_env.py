@@ -76,6 +76,7 @@ class RoboRugbyVecEnv:
         _lib.check(self.lib.rr_set_stats_buffer(h, self.stats.data_ptr()))
         self._bufs = {}
         self.pipeline = 1
+        self._inflight = []
         if pipeline and int(pipeline) > 1:
             self.set_pipeline(pipeline)
 
@@ -98,6 +99,9 @@ class RoboRugbyVecEnv:
     def join(self):
         """Make the current stream wait (on the device) for every group's outstanding launches."""
         _lib.check(self.lib.rr_join(self._h, self._stream()))
+        if self._inflight:
+            # the current stream now waits for the groups; anything it frees after this point is ordered behind them
+            self._inflight = []
 
     # ------------------------------------------------------------------ lifetime
     def close(self):
@@ -227,7 +231,11 @@ class RoboRugbyVecEnv:
             if join:
                 self.join()
             else:
-                self._inflight_actions = actions   # keep the buffer alive until the groups have read it
+                # keep every action buffer alive until the groups have read it: the groups run on the handle's own streams,
+                # which torch's stream-ordered allocator knows nothing about
+                self._inflight.append(actions)
+                if len(self._inflight) > 256:   # a caller that never joins: bound what is kept alive
+                    self.join()
         return b["obs_h"][..., :self.obs_dim], b["obs_g"][..., :self.obs_dim], b["rew"], b["done"]
 
     def step_host(self, actions_host, k, out=None):
