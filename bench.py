@@ -395,7 +395,7 @@ def main():
                                 "actions resident, calls issued back to back, no L2 flush"}
         if rank == 0 and world == 1:
             env.close()   # (its buffers are not needed any more)
-            extras["dqn"] = dqn_rate(dev, envs=16384, steps=60)
+            extras["dqn"] = dqn_rate(dev, envs=65536, steps=40)
 
     if rank == 0:
         peak, peak_src = _peaks()
