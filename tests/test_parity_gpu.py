@@ -810,6 +810,8 @@ def test_gpu_sub_batch_pipeline_is_bit_identical(preset, groups):
     mk = lambda **kw: _venv(V2, N, preset, seed=21, out_dtype=torch.float32, time_limit=True, auto_reset=True, **kw)
     a, b = mk(), mk(pipeline=groups)
     assert b.pipeline == groups
+    flush = torch.zeros(8 << 20, dtype=torch.uint8, device="cuda")
+    b.set_flush_buffer(flush)   # bench.py's L2 hygiene (every group overwrites its share in front of its launch): no effect
     for env in (a, b):   # episode ends (auto-reset) inside the launches
         st = env.get_state(); st["step"][:] = env.max_episode_steps - 1 - (np.arange(N) % (3 * K)); env.set_state(st)
     acts = [torch.randint(0, 8, (K, N, a.num_robots), generator=g, dtype=torch.uint8).cuda() for _ in range(4)]
@@ -835,6 +837,8 @@ def test_gpu_sub_batch_pipeline_is_bit_identical(preset, groups):
     assert ta["episodes"] == tb["episodes"] > 0 and ta["steps"] == tb["steps"] == 4 * K * N
     assert ta["naughty"] == tb["naughty"]
     assert b.launch_count - 1 > a.launch_count - 1   # one kernel per group and call
+    assert int((flush != 0).sum()) > flush.numel() // 2   # every group wrote its share (the launch counter's low byte)
+    b.set_flush_buffer(None)
     b.set_pipeline(1)   # back to one launch per call, same handle
     assert all(same(x, y) for x, y in zip(a.step_k(acts[0], K), b.step_k(acts[0], K)))
 
