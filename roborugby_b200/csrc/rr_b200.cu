@@ -29,7 +29,7 @@ namespace rr {
 // Launch geometry.  One block per SM is the target: its warps are re-synchronised every physics
 // frame so that they share instruction-cache lines, and the batch is spread over all 148 SMs in one
 // wave.  The hot per-env doubles (robot rects) live in shared memory, [field][thread] with the block
-// size as stride: GAME 56 doubles x 448 threads = 196 KB; the cold ones (balls, history slots) in a
+// size as stride: GAME 56 doubles x 384 threads = 168 KB; the cold ones (balls, history slots) in a
 // per-thread local array.
 template <int NH, int NG, int NP, int NN, bool GOALS = false, int MAXB = 0>
 struct Launch {
