@@ -26,11 +26,12 @@
 
 namespace rr {
 
-// Launch geometry.  One block per SM is the target: its warps are re-synchronised every physics
-// frame so that they share instruction-cache lines, and the batch is spread over all 148 SMs in one
-// wave.  The hot per-env doubles (robot rects) live in shared memory, [field][thread] with the block
-// size as stride: GAME 56 doubles x 384 threads = 168 KB; the cold ones (balls, history slots) in a
-// per-thread local array.
+// Launch geometry.  One block is resident per SM: its warps are re-synchronised every physics frame so that they
+// share instruction-cache lines.  A caller that steps one stream-ordered launch at a time gets the batch in one wave
+// over all SMs; with the sub-batch pipeline (rr_set_pipeline) the blocks are launched in groups on the handle's own
+// streams and their number is free (65 536 GAME envs = 171 blocks of 384 threads, which the SMs work off as they
+// become free).  The hot per-env doubles (robot rects) live in shared memory, [field][thread] with the block size as
+// stride: GAME 56 doubles x 384 threads = 168 KB; the cold ones (balls, history slots) in a per-thread local array.
 template <int NH, int NG, int NP, int NN, bool GOALS = false, int MAXB = 0>
 struct Launch {
   static constexpr int R = NH + NG, B = NP + NN;
