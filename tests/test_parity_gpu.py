@@ -488,7 +488,9 @@ def test_gpu_bench_configuration_matches_oracle(oracle, strict, pipeline):
     T = env.max_episode_steps
     st = env.get_state()
     st["step"][:] = (np.arange(N) * 7919) % max(T - 1, 1)     # bench.py's desynchronisation
-    sample = np.unique(np.concatenate([np.arange(0, N, 67), np.nonzero(st["step"] >= T - K)[0][:128]]))[:1024]
+    import os
+    stride = int(os.environ.get("RR_PARITY_STRIDE", "67"))   # a one-off deeper run: RR_PARITY_STRIDE=8 replays 8 192 envs
+    sample = np.unique(np.concatenate([np.arange(0, N, stride), np.nonzero(st["step"] >= T - K)[0][:128]]))[:max(1024, N // stride + 128)]
     assert (st["step"][sample] >= T - K).sum() >= 64, "resets must fall inside the launch for some sampled envs"
     env.set_state(st)
     g = torch.Generator(device="cuda").manual_seed(1)
